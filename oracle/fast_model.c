@@ -1,0 +1,59 @@
+/* oracle/fast_model.c -- TEST INFRASTRUCTURE (CPU oracle). Not part of the shipped product path.
+ *
+ * CPU model of the B200 production ("fast") stream convention, used to pin the CUDA kernel per path.
+ * The reference's pair update (/root/reference/src/mc_simd.rs:9-21) adds sqrt(-ln u1) * (sin 2*pi*u2 + cos 2*pi*u2)
+ * per two time steps, with u1,u2 taken from two 64-bit generator outputs per lane (src/rand32x8.rs:5-21).
+ * The production kernel keeps that estimator but restates it for the GPU's MUFU/ALU pipes:
+ *     sqrt(-ln u1) (sin t + cos t)  ==  sqrt(2 ln 2) * sqrt(-log2 u1) * sin(t + pi/4)         (exact identity)
+ * and draws u1,u2 from ONE 64-bit output (high word -> u1 in (0,1], low word -> the angle), 23 bits each.
+ * The constant sqrt(2 ln 2) is folded into the terminal scale.  This file states that convention on the CPU with
+ * libm (log2f / sqrtf / sinf / exp2f); the GPU differs only by the MUFU approximations (tests give the tolerance).
+ *
+ * One generator stream serves many paths back to back (the per-thread stream of the kernel), instead of a fresh
+ * 256-byte seed per 8 paths (mc_simd.rs:52-54); substreams come from jump()/long_jump() (xoshiro256pp.h).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "xoshiro256pp.h"
+
+static inline float bits_to_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+
+/* one Box-Muller pair in the fast convention: returns sqrt(|log2 u1|) * sin(2*pi*f2 + pi/4) added to acc */
+static inline float fast_pair_increment(xo256_t *g, float acc) {
+    const uint64_t x = xo256pp_next(g);
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    const float f1 = bits_to_float((hi >> 9) | 0x3f800000u);     /* [1,2) */
+    const float f2 = bits_to_float((lo >> 9) | 0x3f800000u);     /* [1,2): one full turn */
+    const float u1 = 2.0f - f1;                                  /* (0,1], exact */
+    const float rad = sqrtf(fabsf(log2f(u1)));
+    const float ang = fmaf(f2, 6.28318530717958647692f, 0.78539816339744830962f);
+    return fmaf(rad, sinf(ang), acc);
+}
+
+/* Run `n_paths` consecutive paths of `half_steps` pairs each from one stream.  state is advanced in place.
+ * out_m[p] = accumulated sum M' of path p (units: sqrt(2 ln 2) smaller than the reference's M). */
+void fast_model_stream_paths(uint64_t state[4], int half_steps, int n_paths, float *out_m) {
+    xo256_t g; memcpy(g.s, state, 32);
+    for (int p = 0; p < n_paths; p++) {
+        float acc = 0.0f;
+        for (int i = 0; i < half_steps; i++) acc = fast_pair_increment(&g, acc);
+        out_m[p] = acc;
+    }
+    memcpy(state, g.s, 32);
+}
+
+/* Terminal-scale constants of the fast convention from the reference's f32 constants (mc_simd.rs:36-45):
+ *   growth = exp(M * sqrt(2)*sidt + steps*nudt) = exp2(M' * c2 + d2),
+ *   c2 = sqrt(2 ln 2) * sqrt(2)*sidt * log2(e),  d2 = steps*nudt * log2(e)   (folded in fp64, rounded once). */
+void fast_model_constants(float vol, float r, float q, float years, float steps, float *c2, float *d2) {
+    const float dt = years / steps;
+    const float nudt = (r - q - 0.5f * (vol * vol)) * dt;
+    const float sidt = vol * sqrtf(dt);
+    const float drift = steps * nudt;
+    const float diff = 1.41421356237309504880f * sidt;
+    *c2 = (float)((double)diff * 1.17741002251547469101 /* sqrt(2 ln 2) */ * 1.44269504088896340736 /* log2 e */);
+    *d2 = (float)((double)drift * 1.44269504088896340736);
+}
+
+float fast_model_growth(float m, float c2, float d2) { return exp2f(fmaf(m, c2, d2)); }

@@ -1,0 +1,148 @@
+"""CPU tests that pin the oracle (oracle/*.c) against the golden vectors and the reference's own tests.
+
+Mirrors the reference's test strategy: in-file #[test] functions comparing one stochastic run with the bs.rs closed
+form under an absolute tolerance (src/mc_simd.rs:781-907, src/mc.rs:75-121) and lane-0 uniform moments
+(src/rand32x8.rs:23-81) -- here with injected seeds, so they are reproducible.
+"""
+import math
+
+import numpy as np
+import pytest
+
+
+def test_xoshiro_known_answer(oracle, xoshiro_kat):
+    out, st = oracle.xoshiro_outputs(xoshiro_kat["state"], 10)
+    assert [str(int(x)) for x in out] == xoshiro_kat["outputs"]
+    assert [str(int(x)) for x in st] == xoshiro_kat["state_after_10"]
+
+
+def test_xoshiro_jump_and_long_jump(oracle, xoshiro_kat):
+    jump = [int(x) for x in xoshiro_kat["jump_poly"]]
+    ljump = [int(x) for x in xoshiro_kat["long_jump_poly"]]
+    s1 = oracle.xoshiro_apply_poly(xoshiro_kat["state"], jump)
+    assert [str(int(x)) for x in s1] == xoshiro_kat["after_jump"]
+    s2 = oracle.xoshiro_apply_poly(s1, jump)
+    assert [str(int(x)) for x in s2] == xoshiro_kat["after_two_jumps"]
+    sl = oracle.xoshiro_apply_poly(xoshiro_kat["state"], ljump)
+    assert [str(int(x)) for x in sl] == xoshiro_kat["after_long_jump"]
+
+
+def test_jump_commutes_with_stepping(oracle, xoshiro_kat):
+    """jump is a polynomial in the transition T, so jump(step^n(s)) == step^n(jump(s))."""
+    jump = [int(x) for x in xoshiro_kat["jump_poly"]]
+    s = [0x1234, 0xdeadbeef, 0x42, 0xabcdef0123456789]
+    _, stepped = oracle.xoshiro_outputs(s, 37)
+    a = oracle.xoshiro_apply_poly(stepped, jump)
+    _, b = oracle.xoshiro_outputs(oracle.xoshiro_apply_poly(s, jump), 37)
+    assert list(a) == list(b)
+
+
+def test_bs_closed_form_matches_golden(oracle, bs_cases):
+    for c in bs_cases:
+        got32 = oracle.bs32(c["bs_function"], *c["params"])
+        got64 = oracle.bs64(c["bs_function"], *c["params"])
+        assert got32 == pytest.approx(c["bs_f32"], abs=2e-5, rel=2e-5), c["reference_test"]
+        assert got64 == pytest.approx(c["bs_f64"], abs=1e-9, rel=1e-9), c["reference_test"]
+        # bs.rs's A&S erf and truncated pi cost at most ~1e-4 against the exact closed form
+        assert got32 == pytest.approx(got64, abs=2e-4), c["reference_test"]
+
+
+def _call_with_bump(oracle, c, seeds):
+    s, k, v, r, t, q = c["params"]
+    fn, h = c["mc_function"], c["bump"]
+    steps, trials = float(c["steps"]), float(c["trials"])
+    if fn in ("call_price", "put_price", "call_price_av", "put_price_av"):
+        return oracle.mc(fn, s, k, v, r, t, q, steps, trials, seeds=seeds)
+    if fn in ("call_delta", "put_delta", "gamma"):
+        return oracle.mc(fn, s, h, k, v, r, t, q, steps, trials, seeds=seeds)
+    if fn == "vega":
+        return oracle.mc(fn, s, k, v, h, r, t, q, steps, trials, seeds=seeds)
+    if fn in ("call_rho", "put_rho"):
+        return oracle.mc(fn, s, k, v, r, h, t, q, steps, trials, seeds=seeds)
+    if fn in ("call_theta", "put_theta"):
+        return oracle.mc(fn, s, k, v, r, t, h, q, steps, trials, seeds=seeds)
+    raise KeyError(fn)
+
+
+def test_reference_tests_replayed_on_oracle(oracle, bs_cases):
+    """All 22 pricing/Greek tests of the reference, same parameters and tolerances, injected seeds."""
+    for i, c in enumerate(bs_cases):
+        seeds = oracle.chunk_seeds(oracle.n_chunks(c["trials"]), 1000 + i)
+        got = _call_with_bump(oracle, c, seeds)
+        err = abs(got - c["bs_f32"])
+        assert (err < c["tolerance"]) if c["strict"] else (err <= c["tolerance"]), (c["reference_test"], got)
+
+
+@pytest.mark.parametrize("samples,limit", [(100, 0.05), (1000, 0.03), (100000, 0.01)])
+def test_uniform_lane0_moments(oracle, samples, limit):
+    """rand32x8.rs:68-81: mean / variance / std of lane 0 within the reference's limits."""
+    u = oracle.uniform_lane_stream(oracle.chunk_seeds(1, 7)[0], 0, samples).astype(np.float64)
+    assert u.min() >= 0.0 and u.max() <= 1.0
+    assert abs(u.mean() - 0.5) <= limit
+    assert abs(u.var() - 1 / 12) <= limit
+    assert abs(u.std() - math.sqrt(1 / 12)) <= limit
+
+
+def test_all_lanes_are_distinct_streams(oracle):
+    seed = oracle.chunk_seeds(1, 11)[0]
+    lanes = [oracle.uniform_lane_stream(seed, l, 64) for l in range(8)]
+    for a in range(8):
+        for b in range(a + 1, 8):
+            assert not np.array_equal(lanes[a], lanes[b])
+
+
+def test_price_within_3se_of_closed_form_on_bench_grid(oracle):
+    """benches/benchmark.rs:10-16 grid (subset), 20000 trials x 100 steps: |MC - BS| <= 3 SE (+ fp floor)."""
+    worst = 0.0
+    for j, spot in enumerate((80.0, 100.0, 110.0, 130.0, 161.0)):
+        seeds = oracle.chunk_seeds(2500, 50 + j)
+        for mult, name in ((1.0, "call_price"), (-1.0, "put_price")):
+            d = oracle.pricing_detail(spot, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 20000.0, mult, seeds)
+            exact = oracle.bs64(name, spot, 110.0, 0.25, 0.05, 0.5, 0.02)
+            z = abs(d["mean"] - exact) / max(d["se"], 1e-4)
+            worst = max(worst, z)
+            assert abs(d["price"] - d["mean"]) <= 2e-3 * max(1.0, abs(d["mean"]))   # f32 sums vs fp64 sums
+    assert worst < 3.5, worst
+
+
+def test_reference_quirks(oracle):
+    """Reproduced on purpose: paths = 8*floor(trials/8) but the mean divides by num_trials (mc_simd.rs:49,77);
+    normals consumed = 2*floor(steps/2) while the drift uses steps (mc_simd.rs:44,47)."""
+    seeds = oracle.chunk_seeds(125, 3)
+    a = oracle.pricing_detail(120.0, 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, 1000.0, 1.0, seeds)
+    b = oracle.pricing_detail(120.0, 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, 1007.0, 1.0, seeds)
+    assert b["price"] == pytest.approx(a["price"] * 1000.0 / 1007.0, rel=1e-5)
+    m_even = oracle.pricing_detail(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 4.0, 64.0, 1.0, seeds[:8], want_paths=True)["m"]
+    m_odd = oracle.pricing_detail(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 5.0, 64.0, 1.0, seeds[:8], want_paths=True)["m"]
+    assert np.array_equal(m_even, m_odd)
+
+
+def test_fast_model_is_the_same_estimator(oracle):
+    """The production stream convention must have the reference's per-pair law: each pair adds a N(0,1) draw in
+    reference units, i.e. Var[M * sqrt(2 ln 2)] = half_steps."""
+    m, _ = oracle.fast_stream_paths([1, 2, 3, 4], 50, 40000)
+    m = m.astype(np.float64) * math.sqrt(2 * math.log(2))
+    assert abs(m.mean()) < 4 * math.sqrt(50 / 40000)
+    assert m.var() == pytest.approx(50.0, rel=0.03)
+    ref = []
+    for c in oracle.chunk_seeds(2000, 5):
+        out = np.empty(8, np.float32)
+        oracle.lib().ref_mc_chunk_sums(c.ctypes.data_as(oracle._u8p), 50, out.ctypes.data_as(oracle._fp))
+        ref.append(out.copy())
+    ref = np.concatenate(ref).astype(np.float64)
+    assert ref.var() == pytest.approx(50.0, rel=0.04)
+    # same kurtosis (gaussian sums): a coarse distributional check
+    k = lambda x: ((x - x.mean()) ** 4).mean() / x.var() ** 2
+    assert k(m) == pytest.approx(3.0, abs=0.15) and k(ref) == pytest.approx(3.0, abs=0.2)
+
+
+def test_cpu_baseline_agrees_with_closed_form(oracle):
+    spots = np.array([90.0, 110.0, 130.0], np.float32)
+    ones = np.ones(3, np.float32)
+    for kind, name in ((0, "call_price"), (1, "put_price"), (2, "call_price"), (3, "put_price")):
+        out, ps = oracle.baseline_price_loop(spots, 110 * ones, .25 * ones, .05 * ones, .5 * ones, .02 * ones,
+                                             100.0, 40000.0, kind)
+        assert ps == 3 * 40000 * 100
+        for s, p in zip(spots, out):
+            exact = oracle.bs64(name, float(s), 110.0, 0.25, 0.05, 0.5, 0.02)
+            assert abs(p - exact) < 0.35, (kind, s, p, exact)   # ~4 SE at 40000 trials (SE <= 0.09)
