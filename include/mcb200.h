@@ -1,0 +1,186 @@
+/* mcb200.h -- C ABI of libmcb200.so, the B200-native (sm_100a) Monte Carlo European-option hot path.
+ *
+ * Drop-in boundary.  The reference (ashayp22/monte-carlo-options-simd) has no FFI layer: its boundary is the Rust
+ * `pub fn` surface of module mc_simd (src/lib.rs:11).  Every mc_simd_* function below replaces the reference function
+ * of the same name with the same f32 parameter list in the same ORDER (the order differs per function); the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.  Plain pointers and sizes only; the
+ * caller owns every buffer; no CPU fallback exists -- without a CUDA device every entry point fails loudly.
+ *
+ * Errors.  The reference's functions return a bare f32 (no Result, src/mc_simd.rs:477-779).  The drop-ins keep that
+ * shape: on failure they return NaN and record a thread-local message readable with mcb200_last_error(); every other
+ * entry point returns an mcb200_status.
+ *
+ * Reference quirks kept on purpose: steps and num_trials are f32; 8*floor(num_trials/8) paths
+ * are simulated but the mean divides by num_trials (mc_simd.rs:49,77); 2*floor(steps/2) normals are consumed while
+ * the drift uses steps (mc_simd.rs:44,47); vega and rho are per 1 point (/200h), theta per year; gamma and vega are
+ * call-only.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcb200_ctx mcb200_ctx;
+
+typedef enum {
+    MCB200_OK = 0,
+    MCB200_ERR_INVALID = 1,     /* bad argument (null pointer, n < 0, steps < 2, num_trials < 8, ...) */
+    MCB200_ERR_CUDA = 2,        /* a CUDA runtime call failed; see mcb200_last_error() */
+    MCB200_ERR_NO_DEVICE = 3,   /* no usable CUDA device (the library has no CPU path) */
+    MCB200_ERR_NOMEM = 4
+} mcb200_status;
+
+/* flags for the price entry points */
+#define MCB200_ANTITHETIC 1u    /* call_price_av / put_price_av estimator (mc_simd.rs:82-149) */
+
+/* ------------------------------------------------------------------ context ------------------------------------ */
+/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams.
+ * Thread slot i of the device uses substream jump^i(long_jump^substream_block(splitmix64(seed))): 2^128 draws per
+ * thread, 2^64 thread slots per block, one block per GPU/rank (replaces per-chunk OS-entropy seeding,
+ * mc_simd.rs:52-54).  Launches continue their substreams, so a fixed (seed, block, call sequence) is reproducible
+ * bit for bit. */
+int mcb200_ctx_create(mcb200_ctx **ctx, int device, uint64_t seed, uint32_t substream_block);
+void mcb200_ctx_destroy(mcb200_ctx *ctx);
+int mcb200_ctx_set_seed(mcb200_ctx *ctx, uint64_t seed, uint32_t substream_block);
+const char *mcb200_last_error(void);
+
+typedef struct {
+    int device, sm_count, ctas_per_sm, threads_per_cta;
+    int grid_slots;              /* resident CTAs the planner fills: sm_count * ctas_per_sm */
+    int64_t pool_threads;        /* generator states held in HBM (32 bytes each) */
+    uint64_t kernel_launches;    /* kernels launched by this context so far */
+    uint64_t seed;
+    uint32_t substream_block;
+    int sm_clock_khz;            /* cudaDevAttrClockRate */
+} mcb200_info;
+int mcb200_ctx_info(mcb200_ctx *ctx, mcb200_info *out);
+
+/* Launch plan for one batch: how (option, trial-slice) work items map onto the persistent grid.  Pure host logic. */
+typedef struct {
+    int n_paths;                 /* 8 * floor(num_trials / 8) */
+    int half_steps;              /* floor(steps) / 2 */
+    int slices;                  /* work items per option */
+    int paths_per_slice;
+    int paths_per_thread;        /* max over threads */
+    int grid;                    /* CTAs launched = min(grid_slots, n_options * slices) */
+    int64_t items;               /* n_options * slices */
+    double path_steps;           /* n_options * n_paths * 2 * half_steps: the throughput numerator */
+} mcb200_plan;
+int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan *out);
+
+/* ------------------------------------------------------------------ batched entry points (new) ----------------- */
+/* Host buffers: inputs are copied to the device, outputs copied back, the call returns when they are valid.
+ * Every option gets its own fresh paths (no sharing across options).  Output pointers may be NULL. */
+int mcb200_price_batch(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                       const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                       float steps, float num_trials, unsigned flags,
+                       float *call_out, float *put_out, float *call_se, float *put_se);
+
+typedef struct { float delta_spot, delta_volatility, delta_risk_free_rate, delta_years_to_expiry; } mcb200_bumps;
+
+/* All ten estimators from ONE set of paths per option (common random numbers across every bump).
+ * Order of out[] / out_se[]: call, put, call_delta, put_delta, gamma, vega, call_rho, put_rho, call_theta, put_theta. */
+#define MCB200_N_GREEK_OUTPUTS 10
+int mcb200_greeks_batch(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                        const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                        float steps, float num_trials, const mcb200_bumps *bumps,
+                        float *const out[MCB200_N_GREEK_OUTPUTS], float *const out_se[MCB200_N_GREEK_OUTPUTS]);
+
+/* Device-resident variants: every pointer is a device pointer on the context's device; work is enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = the context's own stream) and the call does not synchronize. */
+int mcb200_price_batch_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                              const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                              float steps, float num_trials, unsigned flags,
+                              float *call_out, float *put_out, float *call_se, float *put_se, void *cuda_stream);
+int mcb200_greeks_batch_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
+                               const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
+                               const float *dividend_yield, float steps, float num_trials, const mcb200_bumps *bumps,
+                               float *const out[MCB200_N_GREEK_OUTPUTS], float *const out_se[MCB200_N_GREEK_OUTPUTS],
+                               void *cuda_stream);
+
+/* Trials-sharded operation (several GPUs simulate disjoint trial ranges of the same options):
+ *   1. each GPU: mcb200_price_moments_device() -> moments[n][4] fp64 = {sum call, sum call^2, sum put, sum put^2}
+ *   2. caller sums the moment arrays across GPUs (ncclAllReduce / torch.distributed.all_reduce, fp64, sum)
+ *   3. mcb200_price_finalize_device() with the TOTAL number of simulated paths and the total num_trials. */
+int mcb200_price_moments_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
+                                const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
+                                const float *dividend_yield, float steps, float num_trials_local, unsigned flags,
+                                double *moments, void *cuda_stream);
+int mcb200_price_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free_rate, const float *years_to_expiry,
+                                 const double *moments, double total_paths, double total_num_trials,
+                                 float *call_out, float *put_out, float *call_se, float *put_se, void *cuda_stream);
+
+/* ------------------------------------------------------------------ parity / inspection ------------------------ */
+/* Reference-stream mode: consume the generator exactly like the reference (a 256-byte simd_rand seed per 8-path
+ * chunk, two 64-bit outputs per Box-Muller pair, 53-bit -> f64 -> f32 uniforms; rand32x8.rs:5-21, mc_simd.rs:9-21).
+ * chunk_seeds: n * floor(num_trials/8) * 256 bytes (host).  growth_out (host, nullable): n * 8*floor(num_trials/8)
+ * per-path terminal growth factors S_T / spot.  Test-only: this is the one mode that writes path data to HBM. */
+int mcb200_price_batch_refstream(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
+                                 const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
+                                 const float *dividend_yield, float steps, float num_trials, unsigned flags,
+                                 const uint8_t *chunk_seeds, float *call_out, float *put_out, float *call_se,
+                                 float *put_se, float *growth_out);
+int mcb200_greeks_batch_refstream(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
+                                  const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
+                                  const float *dividend_yield, float steps, float num_trials,
+                                  const mcb200_bumps *bumps, const uint8_t *chunk_seeds,
+                                  float *const out[MCB200_N_GREEK_OUTPUTS], float *const out_se[MCB200_N_GREEK_OUTPUTS]);
+/* Production stream with the per-path growth factors dumped (test-only).  growth_out: n * n_paths floats (host). */
+int mcb200_price_batch_dump(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                            const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                            float steps, float num_trials, unsigned flags,
+                            float *call_out, float *put_out, float *call_se, float *put_se, float *growth_out);
+/* Copy generator states [first, first+count) of the pool to the host (4 x u64 per thread slot). */
+int mcb200_ctx_export_states(mcb200_ctx *ctx, int64_t first, int64_t count, uint64_t *states_out);
+
+/* Kernel timing for roofline accounting: when enabled, CUDA events are recorded on the launch stream immediately
+ * before and after every simulate-kernel launch; mcb200_ctx_last_sim_ms() waits for the latest one and returns its
+ * device duration in milliseconds (the fused path kernel alone, without the second-pass kernels). */
+int mcb200_ctx_set_timing(mcb200_ctx *ctx, int enabled);
+int mcb200_ctx_last_sim_ms(mcb200_ctx *ctx, float *ms_out);
+
+/* Pipe-throughput microbenchmarks (MUFU / FMA / ALU / issue) that fix the roofline denominator with measured numbers.
+ * Writes up to `cap` results; returns the number written (negative = error). */
+typedef struct { char name[32]; double ops_per_clk_per_sm; double elapsed_ms; double sm_clock_mhz; } mcb200_pipe_rate;
+int mcb200_microbench(mcb200_ctx *ctx, mcb200_pipe_rate *out, int cap);
+
+/* ------------------------------------------------------------------ the 12 drop-ins ---------------------------- */
+/* Same names, parameter lists and semantics as /root/reference/src/mc_simd.rs:477-779.  They run on a lazily
+ * created process-wide default context (device MCB200_DEVICE or 0, seed MCB200_SEED or a fixed constant), are
+ * blocking and callable from any thread. */
+float mc_simd_call_price(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                         float dividend_yield, float steps, float num_trials);               /* mc_simd.rs:477-498 */
+float mc_simd_put_price(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                        float dividend_yield, float steps, float num_trials);                /* mc_simd.rs:500-521 */
+float mc_simd_call_price_av(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                            float dividend_yield, float steps, float num_trials);            /* mc_simd.rs:523-544 */
+float mc_simd_put_price_av(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                           float dividend_yield, float steps, float num_trials);             /* mc_simd.rs:546-567 */
+float mc_simd_call_delta(float spot, float delta_spot, float strike, float volatility, float risk_free_rate,
+                         float years_to_expiry, float dividend_yield, float steps, float num_trials); /* :569-593 */
+float mc_simd_put_delta(float spot, float delta_spot, float strike, float volatility, float risk_free_rate,
+                        float years_to_expiry, float dividend_yield, float steps, float num_trials);  /* :595-619 */
+float mc_simd_gamma(float spot, float delta_spot, float strike, float volatility, float risk_free_rate,
+                    float years_to_expiry, float dividend_yield, float steps, float num_trials);      /* :621-645 */
+float mc_simd_vega(float spot, float strike, float volatility, float delta_volatility, float risk_free_rate,
+                   float years_to_expiry, float dividend_yield, float steps, float num_trials);       /* :647-671 */
+float mc_simd_call_rho(float spot, float strike, float volatility, float risk_free_rate, float delta_risk_free_rate,
+                       float years_to_expiry, float dividend_yield, float steps, float num_trials);   /* :673-699 */
+float mc_simd_put_rho(float spot, float strike, float volatility, float risk_free_rate, float delta_risk_free_rate,
+                      float years_to_expiry, float dividend_yield, float steps, float num_trials);    /* :701-726 */
+float mc_simd_call_theta(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                         float delta_years_to_expiry, float dividend_yield, float steps, float num_trials); /* :728-753 */
+float mc_simd_put_theta(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
+                        float delta_years_to_expiry, float dividend_yield, float steps, float num_trials);  /* :755-779 */
+
+/* Select / inspect the default context used by the drop-ins (NULL restores lazy creation). */
+int mcb200_default_ctx(mcb200_ctx **out);
+int mcb200_default_ctx_reset(int device, uint64_t seed, uint32_t substream_block);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

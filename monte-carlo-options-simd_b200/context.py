@@ -1,0 +1,178 @@
+"""Context: one device + stream + pool of per-thread xoshiro256++ substreams (wraps mcb200_ctx)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class Context:
+    """Owns an mcb200_ctx.  All batched entry points of the C ABI are methods here.
+
+    substream_block selects the long_jump block of generator substreams: use the global rank of the GPU so that
+    GPUs / processes never share draws.
+    """
+
+    def __init__(self, device=0, seed=0x5EED5EED5EED5EED, substream_block=0):
+        self._h = C.c_void_p()
+        N.check(N.lib().mcb200_ctx_create(C.byref(self._h), int(device), int(seed) & (2 ** 64 - 1),
+                                          int(substream_block)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().mcb200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ inspection
+    def info(self):
+        inf = N.Info()
+        N.check(N.lib().mcb200_ctx_info(self._h, C.byref(inf)))
+        return {k: getattr(inf, k) for k, _ in N.Info._fields_}
+
+    def set_seed(self, seed, substream_block=0):
+        N.check(N.lib().mcb200_ctx_set_seed(self._h, int(seed) & (2 ** 64 - 1), int(substream_block)))
+
+    def plan(self, n_options, steps, num_trials):
+        return plan_query(n_options, steps, num_trials, self.info()["grid_slots"])
+
+    def export_states(self, first, count):
+        out = np.empty((count, 4), np.uint64)
+        N.check(N.lib().mcb200_ctx_export_states(self._h, first, count, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def set_timing(self, enabled=True):
+        N.check(N.lib().mcb200_ctx_set_timing(self._h, 1 if enabled else 0))
+
+    def last_sim_ms(self):
+        ms = C.c_float()
+        N.check(N.lib().mcb200_ctx_last_sim_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def microbench(self):
+        buf = (N.PipeRate * 32)()
+        n = N.lib().mcb200_microbench(self._h, buf, 32)
+        if n < 0:
+            raise N.Mcb200Error(-n, N.last_error())
+        return [dict(name=buf[i].name.decode(), ops_per_clk_per_sm=buf[i].ops_per_clk_per_sm,
+                     elapsed_ms=buf[i].elapsed_ms, sm_clock_mhz=buf[i].sm_clock_mhz) for i in range(n)]
+
+    # ------------------------------------------------------------------ host-buffer batches
+    @staticmethod
+    def _inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield):
+        n = max(np.size(a) for a in (spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield))
+        arrs = [N.as_f32(a, n) for a in (spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)]
+        arrs = [np.full(n, a[0], np.float32) if a.size == 1 and n > 1 else a for a in arrs]
+        for a in arrs:
+            if a.size != n:
+                raise ValueError("option arrays must have the same length")
+        return n, arrs
+
+    def price_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                    num_trials, antithetic=False):
+        """Call and put prices (+ standard errors) for n options from fresh paths per option."""
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        N.check(N.lib().mcb200_price_batch(self._h, n, *[N.fptr(a) for a in arrs], steps, num_trials,
+                                           N.ANTITHETIC if antithetic else 0, *[N.fptr(o) for o in out]))
+        return dict(call=out[0], put=out[1], call_se=out[2], put_se=out[3])
+
+    def greeks_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                     num_trials, delta_spot=0.01, delta_volatility=0.01, delta_risk_free_rate=0.01,
+                     delta_years_to_expiry=0.001):
+        """Prices and all Greeks by central differences on common random numbers, one pass."""
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        vals = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        ses = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        bumps = N.Bumps(delta_spot, delta_volatility, delta_risk_free_rate, delta_years_to_expiry)
+        N.check(N.lib().mcb200_greeks_batch(self._h, n, *[N.fptr(a) for a in arrs], steps, num_trials, C.byref(bumps),
+                                            N._GreekOut(*[N.fptr(v) for v in vals]),
+                                            N._GreekOut(*[N.fptr(s) for s in ses])))
+        res = {name: vals[i] for i, name in enumerate(N.GREEK_NAMES)}
+        res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
+        return res
+
+    # ------------------------------------------------------------------ parity / inspection modes
+    def price_batch_refstream(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                              num_trials, chunk_seeds, antithetic=False, want_growth=False):
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        seeds = np.ascontiguousarray(chunk_seeds, np.uint8)
+        n_chunks = int(num_trials) // 8
+        if seeds.size != n * n_chunks * 256:
+            raise ValueError("chunk_seeds must hold n * floor(num_trials/8) * 256 bytes")
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        growth = np.empty((n, n_chunks * 8), np.float32) if want_growth else None
+        N.check(N.lib().mcb200_price_batch_refstream(
+            self._h, n, *[N.fptr(a) for a in arrs], steps, num_trials, N.ANTITHETIC if antithetic else 0,
+            seeds.ctypes.data_as(C.POINTER(C.c_uint8)), *[N.fptr(o) for o in out], N.fptr(growth)))
+        return dict(call=out[0], put=out[1], call_se=out[2], put_se=out[3], growth=growth)
+
+    def greeks_batch_refstream(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                               num_trials, chunk_seeds, delta_spot=0.01, delta_volatility=0.01,
+                               delta_risk_free_rate=0.01, delta_years_to_expiry=0.001):
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        seeds = np.ascontiguousarray(chunk_seeds, np.uint8)
+        if seeds.size != n * (int(num_trials) // 8) * 256:
+            raise ValueError("chunk_seeds must hold n * floor(num_trials/8) * 256 bytes")
+        vals = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        ses = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        bumps = N.Bumps(delta_spot, delta_volatility, delta_risk_free_rate, delta_years_to_expiry)
+        N.check(N.lib().mcb200_greeks_batch_refstream(
+            self._h, n, *[N.fptr(a) for a in arrs], steps, num_trials, C.byref(bumps),
+            seeds.ctypes.data_as(C.POINTER(C.c_uint8)), N._GreekOut(*[N.fptr(v) for v in vals]),
+            N._GreekOut(*[N.fptr(s) for s in ses])))
+        res = {name: vals[i] for i, name in enumerate(N.GREEK_NAMES)}
+        res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
+        return res
+
+    def price_batch_dump(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                         num_trials, antithetic=False):
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        growth = np.empty((n, (int(num_trials) // 8) * 8), np.float32)
+        N.check(N.lib().mcb200_price_batch_dump(self._h, n, *[N.fptr(a) for a in arrs], steps, num_trials,
+                                                N.ANTITHETIC if antithetic else 0, *[N.fptr(o) for o in out],
+                                                N.fptr(growth)))
+        return dict(call=out[0], put=out[1], call_se=out[2], put_se=out[3], growth=growth)
+
+    # ------------------------------------------------------------------ device-resident batches (raw pointers)
+    def price_batch_device(self, n, in_ptrs, steps, num_trials, out_ptrs, antithetic=False, stream=0):
+        """in_ptrs: 6 device pointers (spot, strike, vol, rate, years, div); out_ptrs: call, put, call_se, put_se
+        (0 = skip).  Enqueues on `stream` (a cudaStream_t as int; 0 = the context's stream) without synchronizing."""
+        N.check(N.lib().mcb200_price_batch_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps, num_trials,
+                                                  N.ANTITHETIC if antithetic else 0,
+                                                  *[C.c_void_p(p) for p in out_ptrs], C.c_void_p(stream)))
+
+    def greeks_batch_device(self, n, in_ptrs, steps, num_trials, bumps, out_ptrs, se_ptrs, stream=0):
+        b = N.Bumps(*bumps)
+        N.check(N.lib().mcb200_greeks_batch_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps, num_trials,
+                                                   C.byref(b), N._VoidOut(*out_ptrs), N._VoidOut(*se_ptrs),
+                                                   C.c_void_p(stream)))
+
+    def price_moments_device(self, n, in_ptrs, steps, num_trials_local, moments_ptr, antithetic=False, stream=0):
+        N.check(N.lib().mcb200_price_moments_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps,
+                                                    num_trials_local, N.ANTITHETIC if antithetic else 0,
+                                                    C.c_void_p(moments_ptr), C.c_void_p(stream)))
+
+    def price_finalize_device(self, n, rate_ptr, years_ptr, moments_ptr, total_paths, total_num_trials, out_ptrs,
+                              stream=0):
+        N.check(N.lib().mcb200_price_finalize_device(self._h, n, C.c_void_p(rate_ptr), C.c_void_p(years_ptr),
+                                                     C.c_void_p(moments_ptr), float(total_paths),
+                                                     float(total_num_trials), *[C.c_void_p(p) for p in out_ptrs],
+                                                     C.c_void_p(stream)))
+
+
+def plan_query(n_options, steps, num_trials, grid_slots):
+    """Launch plan (pure host logic; works without a GPU)."""
+    p = N.Plan()
+    st = N.lib().mcb200_plan_query(int(n_options), float(steps), float(num_trials), int(grid_slots), C.byref(p))
+    if st != 0:
+        raise N.Mcb200Error(st, "invalid plan request")
+    return {k: getattr(p, k) for k, _ in N.Plan._fields_}

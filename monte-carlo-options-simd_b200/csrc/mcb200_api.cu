@@ -1,0 +1,633 @@
+// mcb200_api.cu -- host runtime and C ABI of libmcb200.so (declared in include/mcb200.h).
+//
+// Replaces, for the hot path only, the Rust `pub fn` surface of the reference's mc_simd module
+// (/root/reference/src/mc_simd.rs:477-779) and its rayon/thread_rng plumbing (mc_simd.rs:49-54,71-78):
+//   context  = device + stream + HBM pool of per-thread xoshiro256++ substreams + pinned staging,
+//   planner  = mcb200_plan.cpp, kernels = mcb200_kernels.cuh.
+// There is no CPU path: without a CUDA device every entry point reports MCB200_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <cuda_runtime.h>
+#include "../../include/mcb200.h"
+#include "../../include/xoshiro256_jump_tables.h"
+#include "mcb200_kernels.cuh"
+#include "mcb200_plan.h"
+
+namespace mcb200 {
+
+int run_microbench(cudaStream_t st, int sm_count, mcb200_pipe_rate* out, int cap);   // mcb200_microbench.cu
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ host xoshiro (seeding only)
+struct HostXo { uint64_t s[4]; };
+static inline uint64_t h_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline void h_step(HostXo& g) {
+    const uint64_t t = g.s[1] << 17;
+    g.s[2] ^= g.s[0]; g.s[3] ^= g.s[1]; g.s[1] ^= g.s[2]; g.s[0] ^= g.s[3]; g.s[2] ^= t; g.s[3] = h_rotl(g.s[3], 45);
+}
+static void h_apply_poly(HostXo& g, const unsigned long long poly[4]) {
+    uint64_t a[4] = {0, 0, 0, 0};
+    for (int w = 0; w < 4; ++w)
+        for (int b = 0; b < 64; ++b) {
+            if (poly[w] & (1ull << b)) for (int k = 0; k < 4; ++k) a[k] ^= g.s[k];
+            h_step(g);
+        }
+    for (int k = 0; k < 4; ++k) g.s[k] = a[k];
+}
+static inline uint64_t h_splitmix(uint64_t& x) {
+    uint64_t z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace mcb200
+
+using namespace mcb200;
+
+// ------------------------------------------------------------------------------------------------ context
+struct mcb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int ctas_per_sm = 0;          // resident 256-thread CTAs per SM the planner assumes (min over kernel variants used)
+    int grid_slots = 0;
+    int clock_khz = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t seed = 0;
+    uint32_t block = 0;
+    uint64_t* pool = nullptr;     // grid_slots * kThreads states
+    int64_t pool_threads = 0;
+    uint64_t* d_jump = nullptr;   // jump polynomial table
+    double* partials = nullptr; size_t partials_cap = 0;      // doubles
+    double* moments = nullptr; size_t moments_cap = 0;        // doubles
+    float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned host / device)
+    uint64_t launches = 0;
+    bool timing = false; bool timed_once = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+};
+
+static int ensure(double** p, size_t* cap, size_t need) {
+    if (*cap >= need) return MCB200_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 2 + 1024;
+    CU(cudaMalloc((void**)p, want * sizeof(double)));
+    *cap = want;
+    return MCB200_OK;
+}
+
+static int ensure_stage(mcb200_ctx* c, size_t need_floats) {
+    if (c->stage_cap >= need_floats) return MCB200_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->h_stage = nullptr; c->d_stage = nullptr; c->stage_cap = 0;
+    size_t want = need_floats + need_floats / 2 + 4096;
+    CU(cudaHostAlloc((void**)&c->h_stage, want * sizeof(float), cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&c->d_stage, want * sizeof(float)));
+    c->stage_cap = want;
+    return MCB200_OK;
+}
+
+static int seed_pool(mcb200_ctx* c) {
+    uint64_t x = c->seed;
+    HostXo base;
+    for (int k = 0; k < 4; ++k) base.s[k] = h_splitmix(x);
+    for (uint32_t b = 0; b < c->block; ++b) h_apply_poly(base, XOSHIRO256_LONG_JUMP);
+    const ulonglong4 bs = make_ulonglong4(base.s[0], base.s[1], base.s[2], base.s[3]);
+    const int threads = 128;
+    const int blocks = (int)((c->pool_threads + threads - 1) / threads);
+    seed_pool_kernel<<<blocks, threads, 0, c->stream>>>(c->pool, (int)c->pool_threads, 0ull, bs, c->d_jump,
+                                                         XOSHIRO256_JUMP_POW2_COUNT);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return MCB200_OK;
+}
+
+template <typename K>
+static int occupancy(K kernel, int* out) {
+    int n = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0));
+    *out = n;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, uint32_t substream_block) {
+    if (!out) return fail(MCB200_ERR_INVALID, "mcb200_ctx_create: null output pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(MCB200_ERR_NO_DEVICE, "no CUDA device (%s); libmcb200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n_dev) return fail(MCB200_ERR_INVALID, "device %d out of range [0,%d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MCB200_ERR_NO_DEVICE, "device %d is sm_%d%d; libmcb200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    mcb200_ctx* c = new (std::nothrow) mcb200_ctx();
+    if (!c) return fail(MCB200_ERR_NOMEM, "out of host memory");
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->seed = seed; c->block = substream_block;
+    cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
+    int rc = MCB200_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "stream create failed"); break; }
+        int occ_price = 0, occ_av = 0, occ_greeks = 0;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_PRICE, false, 8>, &occ_price))) break;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_AV, false, 8>, &occ_av))) break;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_GREEKS, false, 8>, &occ_greeks))) break;
+        int occ = occ_price < occ_av ? occ_price : occ_av;
+        if (occ_greeks < occ) occ = occ_greeks;
+        if (occ < 1) { rc = fail(MCB200_ERR_CUDA, "kernel occupancy query returned %d", occ); break; }
+        c->ctas_per_sm = occ;
+        c->grid_slots = c->sm_count * occ;
+        c->pool_threads = (int64_t)c->grid_slots * kThreads;
+        if (cudaMalloc((void**)&c->pool, (size_t)c->pool_threads * 32) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "pool alloc failed"); break; }
+        if (cudaMalloc((void**)&c->d_jump, sizeof(XOSHIRO256_JUMP_POW2)) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "jump table alloc failed"); break; }
+        if (cudaMemcpy(c->d_jump, XOSHIRO256_JUMP_POW2, sizeof(XOSHIRO256_JUMP_POW2), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "jump table copy failed"); break; }
+        if ((rc = seed_pool(c))) break;
+    } while (0);
+    if (rc != MCB200_OK) { mcb200_ctx_destroy(c); return rc; }
+    *out = c;
+    return MCB200_OK;
+}
+
+extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->pool) cudaFree(c->pool);
+    if (c->d_jump) cudaFree(c->d_jump);
+    if (c->partials) cudaFree(c->partials);
+    if (c->moments) cudaFree(c->moments);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    delete c;
+}
+
+extern "C" int mcb200_ctx_set_seed(mcb200_ctx* c, uint64_t seed, uint32_t substream_block) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->seed = seed; c->block = substream_block;
+    return seed_pool(c);
+}
+
+extern "C" const char* mcb200_last_error(void) { return g_err; }
+
+extern "C" int mcb200_ctx_info(mcb200_ctx* c, mcb200_info* out) {
+    if (!c || !out) return fail(MCB200_ERR_INVALID, "null argument");
+    out->device = c->device; out->sm_count = c->sm_count; out->ctas_per_sm = c->ctas_per_sm;
+    out->threads_per_cta = kThreads; out->grid_slots = c->grid_slots; out->pool_threads = c->pool_threads;
+    out->kernel_launches = c->launches; out->seed = c->seed; out->substream_block = c->block;
+    out->sm_clock_khz = c->clock_khz;
+    return MCB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+struct Request {
+    int n = 0;
+    OptionArrays opt{};            // device pointers
+    float steps = 0, num_trials = 0;
+    int payoff = PAYOFF_PRICE;
+    int stream_mode = STREAM_FAST;
+    bool dump = false;
+    Bumps bumps{1.0f, 1.0f, 1.0f, 1.0f};
+    const uint64_t* chunk_seeds = nullptr;   // device
+    float* growth_out = nullptr;             // device
+};
+
+template <int STREAM, int PAYOFF, bool DUMP>
+static void launch_sim(const SimArgs& a, int grid, cudaStream_t st) {
+    simulate_kernel<STREAM, PAYOFF, DUMP, 8><<<grid, kThreads, 0, st>>>(a);
+}
+
+// Simulate and reduce to per-option moment sums in `moments_out` (device, [n][2*n_est] doubles).
+static int run_moments(mcb200_ctx* c, const Request& rq, double* moments_out, cudaStream_t st, mcb200_plan* plan_out) {
+    mcb200_plan pl;
+    int rc = make_plan(rq.n, rq.steps, rq.num_trials, c->grid_slots, &pl);
+    if (rc != MCB200_OK) return fail(rc, "invalid request: n=%d steps=%g num_trials=%g", rq.n, rq.steps, rq.num_trials);
+    if (plan_out) *plan_out = pl;
+    const int n_est = rq.payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
+    const int n_acc = 2 * n_est;
+    if (rq.n == 0) return MCB200_OK;
+    if (pl.n_paths == 0) {
+        CU(cudaMemsetAsync(moments_out, 0, sizeof(double) * (size_t)rq.n * n_acc, st));
+        return MCB200_OK;
+    }
+    if ((rc = ensure(&c->partials, &c->partials_cap, (size_t)pl.items * n_acc))) return rc;
+    SimArgs a{};
+    a.opt = rq.opt; a.n_options = rq.n; a.n_paths = pl.n_paths; a.half_steps = pl.half_steps; a.steps = rq.steps;
+    a.slices = pl.slices; a.paths_per_slice = pl.paths_per_slice; a.bumps = rq.bumps; a.pool = c->pool;
+    a.chunk_seeds = rq.chunk_seeds; a.partials = c->partials; a.growth_out = rq.growth_out;
+    const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
+    if (c->timing) CU(cudaEventRecord(c->ev0, st));
+    switch (key) {
+        case 0:   launch_sim<STREAM_FAST, PAYOFF_PRICE, false>(a, pl.grid, st); break;
+        case 1:   launch_sim<STREAM_FAST, PAYOFF_PRICE, true>(a, pl.grid, st); break;
+        case 10:  launch_sim<STREAM_FAST, PAYOFF_AV, false>(a, pl.grid, st); break;
+        case 11:  launch_sim<STREAM_FAST, PAYOFF_AV, true>(a, pl.grid, st); break;
+        case 20:  launch_sim<STREAM_FAST, PAYOFF_GREEKS, false>(a, pl.grid, st); break;
+        case 100: launch_sim<STREAM_REF, PAYOFF_PRICE, false>(a, pl.grid, st); break;
+        case 101: launch_sim<STREAM_REF, PAYOFF_PRICE, true>(a, pl.grid, st); break;
+        case 110: launch_sim<STREAM_REF, PAYOFF_AV, false>(a, pl.grid, st); break;
+        case 111: launch_sim<STREAM_REF, PAYOFF_AV, true>(a, pl.grid, st); break;
+        case 120: launch_sim<STREAM_REF, PAYOFF_GREEKS, false>(a, pl.grid, st); break;
+        default: return fail(MCB200_ERR_INVALID, "unsupported kernel variant %d", key);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    if (c->timing) { CU(cudaEventRecord(c->ev1, st)); c->timed_once = true; }
+    const int total = rq.n * n_acc;
+    sum_slices_kernel<<<(total + 255) / 256, 256, 0, st>>>(c->partials, rq.n, pl.slices, n_acc, moments_out);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MCB200_OK;
+}
+
+static int run_finalize(mcb200_ctx* c, int n, int n_est, const double* moments, double n_paths, double num_trials,
+                        const float* rate, const float* years, Bumps bumps, float* const* out, float* const* out_se,
+                        cudaStream_t st) {
+    if (n == 0) return MCB200_OK;
+    FinalizeArgs f{};
+    f.moments = moments; f.n_options = n; f.n_est = n_est; f.n_paths = n_paths; f.num_trials = num_trials;
+    f.rate = rate; f.years = years; f.bumps = bumps;
+    for (int e = 0; e < EST_COUNT_GREEKS; ++e) {
+        f.out[e] = (e < n_est && out) ? out[e] : nullptr;
+        f.out_se[e] = (e < n_est && out_se) ? out_se[e] : nullptr;
+    }
+    finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(f);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MCB200_OK;
+}
+
+static int check_common(mcb200_ctx* c, int n, const float* const* arrays, int n_arrays) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    if (n < 0) return fail(MCB200_ERR_INVALID, "n = %d < 0", n);
+    if (n > 0)
+        for (int i = 0; i < n_arrays; ++i)
+            if (!arrays[i]) return fail(MCB200_ERR_INVALID, "null input array %d", i);
+    return MCB200_OK;
+}
+
+static Bumps to_bumps(const mcb200_bumps* b) {
+    return Bumps{b->delta_spot, b->delta_volatility, b->delta_risk_free_rate, b->delta_years_to_expiry};
+}
+
+// Device-resident core shared by every entry point.
+static int run_device(mcb200_ctx* c, const Request& rq, float* const* out, float* const* out_se, cudaStream_t st) {
+    const int n_est = rq.payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
+    int rc = ensure(&c->moments, &c->moments_cap, (size_t)(rq.n > 0 ? rq.n : 1) * 2 * n_est);
+    if (rc) return rc;
+    mcb200_plan pl;
+    if ((rc = run_moments(c, rq, c->moments, st, &pl))) return rc;
+    return run_finalize(c, rq.n, n_est, c->moments, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate,
+                        rq.opt.years, rq.bumps, out, out_se, st);
+}
+
+extern "C" int mcb200_price_batch_device(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                         const float* vol, const float* rate, const float* years, const float* div,
+                                         float steps, float num_trials, unsigned flags, float* call_out,
+                                         float* put_out, float* call_se, float* put_se, void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials;
+    rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return run_device(c, rq, out, se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+extern "C" int mcb200_greeks_batch_device(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                          const float* vol, const float* rate, const float* years, const float* div,
+                                          float steps, float num_trials, const mcb200_bumps* bumps,
+                                          float* const out[MCB200_N_GREEK_OUTPUTS],
+                                          float* const out_se[MCB200_N_GREEK_OUTPUTS], void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials;
+    rq.payoff = PAYOFF_GREEKS; rq.bumps = to_bumps(bumps);
+    return run_device(c, rq, out, out_se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+extern "C" int mcb200_price_moments_device(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                           const float* vol, const float* rate, const float* years, const float* div,
+                                           float steps, float num_trials_local, unsigned flags, double* moments,
+                                           void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (n > 0 && !moments) return fail(MCB200_ERR_INVALID, "null moments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps;
+    rq.num_trials = num_trials_local;
+    rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
+    return run_moments(c, rq, moments, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
+}
+
+extern "C" int mcb200_price_finalize_device(mcb200_ctx* c, int n, const float* rate, const float* years,
+                                            const double* moments, double total_paths, double total_num_trials,
+                                            float* call_out, float* put_out, float* call_se, float* put_se,
+                                            void* cuda_stream) {
+    const float* in[2] = {rate, years};
+    int rc = check_common(c, n, in, 2);
+    if (rc) return rc;
+    if (n > 0 && !moments) return fail(MCB200_ERR_INVALID, "null moments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return run_finalize(c, n, EST_COUNT_PRICE, moments, total_paths, total_num_trials, rate, years,
+                        Bumps{1, 1, 1, 1}, out, se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer entry points
+// Staging layout (floats): [6][n] inputs | [2*n_est][n] outputs (value rows then SE rows).
+static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps, float num_trials, int payoff,
+                    int stream_mode, Bumps bumps, const uint8_t* chunk_seeds_host, float* const* out,
+                    float* const* out_se, float* growth_out_host, bool dump) {
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    mcb200_plan pl;
+    rc = make_plan(n, steps, num_trials, c->grid_slots, &pl);
+    if (rc) return fail(rc, "invalid request: n=%d steps=%g num_trials=%g", n, steps, num_trials);
+    if (n == 0) return MCB200_OK;
+    const int n_est = payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
+    const size_t in_f = 6 * (size_t)n, out_f = 2 * (size_t)n_est * n;
+    if ((rc = ensure_stage(c, in_f + out_f))) return rc;
+    for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
+    Request rq;
+    rq.n = n; rq.steps = steps; rq.num_trials = num_trials; rq.payoff = payoff; rq.stream_mode = stream_mode;
+    rq.bumps = bumps; rq.dump = dump;
+    const float* d = c->d_stage;
+    rq.opt = OptionArrays{d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n};
+    uint64_t* d_seeds = nullptr; float* d_growth = nullptr;
+    const size_t seed_bytes = (size_t)n * (pl.n_paths / 8) * 256, growth_bytes = (size_t)n * pl.n_paths * sizeof(float);
+    if (stream_mode == STREAM_REF) {
+        if (!chunk_seeds_host) return fail(MCB200_ERR_INVALID, "null chunk_seeds");
+        if (seed_bytes) {
+            CU(cudaMalloc((void**)&d_seeds, seed_bytes));
+            cudaError_t e = cudaMemcpyAsync(d_seeds, chunk_seeds_host, seed_bytes, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { cudaFree(d_seeds); return fail(MCB200_ERR_CUDA, "seed copy: %s", cudaGetErrorString(e)); }
+        }
+        rq.chunk_seeds = d_seeds;
+    }
+    if (dump && growth_bytes) {
+        cudaError_t e = cudaMalloc((void**)&d_growth, growth_bytes);
+        if (e != cudaSuccess) { if (d_seeds) cudaFree(d_seeds); return fail(MCB200_ERR_NOMEM, "growth buffer: %s", cudaGetErrorString(e)); }
+        rq.growth_out = d_growth;
+    }
+    float* d_out[EST_COUNT_GREEKS]; float* d_se[EST_COUNT_GREEKS];
+    for (int e = 0; e < n_est; ++e) {
+        d_out[e] = c->d_stage + in_f + (size_t)e * n;
+        d_se[e] = c->d_stage + in_f + (size_t)(n_est + e) * n;
+    }
+    rc = run_device(c, rq, d_out, d_se, st);
+    if (rc == MCB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(c->h_stage + in_f, c->d_stage + in_f, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && dump && growth_bytes)
+            e = cudaMemcpyAsync(growth_out_host, d_growth, growth_bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(MCB200_ERR_CUDA, "result copy / sync: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    if (d_seeds) cudaFree(d_seeds);
+    if (d_growth) cudaFree(d_growth);
+    if (rc != MCB200_OK) return rc;
+    for (int e = 0; e < n_est; ++e) {
+        if (out && out[e]) std::memcpy(out[e], c->h_stage + in_f + (size_t)e * n, sizeof(float) * n);
+        if (out_se && out_se[e]) std::memcpy(out_se[e], c->h_stage + in_f + (size_t)(n_est + e) * n, sizeof(float) * n);
+    }
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_price_batch(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                                  const float* rate, const float* years, const float* div, float steps,
+                                  float num_trials, unsigned flags, float* call_out, float* put_out, float* call_se,
+                                  float* put_se) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return run_host(c, n, in, steps, num_trials, (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE, STREAM_FAST,
+                    Bumps{1, 1, 1, 1}, nullptr, out, se, nullptr, false);
+}
+
+extern "C" int mcb200_greeks_batch(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                                   const float* rate, const float* years, const float* div, float steps,
+                                   float num_trials, const mcb200_bumps* bumps,
+                                   float* const out[MCB200_N_GREEK_OUTPUTS],
+                                   float* const out_se[MCB200_N_GREEK_OUTPUTS]) {
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    return run_host(c, n, in, steps, num_trials, PAYOFF_GREEKS, STREAM_FAST, to_bumps(bumps), nullptr, out, out_se,
+                    nullptr, false);
+}
+
+extern "C" int mcb200_price_batch_refstream(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                            const float* vol, const float* rate, const float* years,
+                                            const float* div, float steps, float num_trials, unsigned flags,
+                                            const uint8_t* chunk_seeds, float* call_out, float* put_out,
+                                            float* call_se, float* put_se, float* growth_out) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return run_host(c, n, in, steps, num_trials, (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE, STREAM_REF,
+                    Bumps{1, 1, 1, 1}, chunk_seeds, out, se, growth_out, growth_out != nullptr);
+}
+
+extern "C" int mcb200_greeks_batch_refstream(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                             const float* vol, const float* rate, const float* years,
+                                             const float* div, float steps, float num_trials,
+                                             const mcb200_bumps* bumps, const uint8_t* chunk_seeds,
+                                             float* const out[MCB200_N_GREEK_OUTPUTS],
+                                             float* const out_se[MCB200_N_GREEK_OUTPUTS]) {
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    return run_host(c, n, in, steps, num_trials, PAYOFF_GREEKS, STREAM_REF, to_bumps(bumps), chunk_seeds, out, out_se,
+                    nullptr, false);
+}
+
+extern "C" int mcb200_price_batch_dump(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                       const float* vol, const float* rate, const float* years, const float* div,
+                                       float steps, float num_trials, unsigned flags, float* call_out, float* put_out,
+                                       float* call_se, float* put_se, float* growth_out) {
+    if (!growth_out) return fail(MCB200_ERR_INVALID, "null growth_out");
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return run_host(c, n, in, steps, num_trials, (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE, STREAM_FAST,
+                    Bumps{1, 1, 1, 1}, nullptr, out, se, growth_out, true);
+}
+
+extern "C" int mcb200_ctx_export_states(mcb200_ctx* c, int64_t first, int64_t count, uint64_t* states_out) {
+    if (!c || !states_out) return fail(MCB200_ERR_INVALID, "null argument");
+    if (first < 0 || count < 0 || first + count > c->pool_threads)
+        return fail(MCB200_ERR_INVALID, "state range [%lld,%lld) outside pool of %lld", (long long)first,
+                    (long long)(first + count), (long long)c->pool_threads);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(states_out, c->pool + 4 * first, (size_t)count * 32, cudaMemcpyDeviceToHost));
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_ctx_set_timing(mcb200_ctx* c, int enabled) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (enabled && !c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); }
+    c->timing = enabled != 0;
+    c->timed_once = false;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_ctx_last_sim_ms(mcb200_ctx* c, float* ms_out) {
+    if (!c || !ms_out) return fail(MCB200_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->timing || !c->timed_once) return fail(MCB200_ERR_INVALID, "no timed simulate-kernel launch recorded");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_microbench(mcb200_ctx* c, mcb200_pipe_rate* out, int cap) {
+    if (!c || !out || cap <= 0) return -fail(MCB200_ERR_INVALID, "bad microbench arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cudaSetDevice(c->device) != cudaSuccess) return -fail(MCB200_ERR_CUDA, "cudaSetDevice failed");
+    int n = run_microbench(c->stream, c->sm_count, out, cap);
+    if (n < 0) return -fail(MCB200_ERR_CUDA, "microbench failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->launches += 2 * (uint64_t)n;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ default context + drop-ins
+static mcb200_ctx* g_default = nullptr;
+static std::mutex g_default_mu;
+
+extern "C" int mcb200_default_ctx(mcb200_ctx** out) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default) {
+        const char* dev = std::getenv("MCB200_DEVICE");
+        const char* seed = std::getenv("MCB200_SEED");
+        const char* blk = std::getenv("MCB200_SUBSTREAM_BLOCK");
+        int rc = mcb200_ctx_create(&g_default, dev ? std::atoi(dev) : 0,
+                                   seed ? std::strtoull(seed, nullptr, 0) : 0x5EED5EED5EED5EEDull,
+                                   blk ? (uint32_t)std::strtoul(blk, nullptr, 0) : 0u);
+        if (rc != MCB200_OK) return rc;
+    }
+    if (out) *out = g_default;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_default_ctx_reset(int device, uint64_t seed, uint32_t substream_block) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (g_default) { mcb200_ctx_destroy(g_default); g_default = nullptr; }
+    return mcb200_ctx_create(&g_default, device, seed, substream_block);
+}
+
+static const float kNaN = std::numeric_limits<float>::quiet_NaN();
+
+// One option through the batched path; `which` picks the estimator to return.
+static float dropin_price(float spot, float strike, float vol, float rate, float years, float div, float steps,
+                          float num_trials, unsigned flags, int which) {
+    mcb200_ctx* c = nullptr;
+    if (mcb200_default_ctx(&c) != MCB200_OK) return kNaN;
+    float outv[2] = {kNaN, kNaN};
+    int rc = mcb200_price_batch(c, 1, &spot, &strike, &vol, &rate, &years, &div, steps, num_trials, flags, &outv[0],
+                                &outv[1], nullptr, nullptr);
+    return rc == MCB200_OK ? outv[which] : kNaN;
+}
+
+static float dropin_greek(float spot, float strike, float vol, float rate, float years, float div, float steps,
+                          float num_trials, mcb200_bumps bumps, int which) {
+    mcb200_ctx* c = nullptr;
+    if (mcb200_default_ctx(&c) != MCB200_OK) return kNaN;
+    float vals[MCB200_N_GREEK_OUTPUTS];
+    float* out[MCB200_N_GREEK_OUTPUTS];
+    for (int e = 0; e < MCB200_N_GREEK_OUTPUTS; ++e) { vals[e] = kNaN; out[e] = (e == which) ? &vals[e] : nullptr; }
+    int rc = mcb200_greeks_batch(c, 1, &spot, &strike, &vol, &rate, &years, &div, steps, num_trials, &bumps, out, nullptr);
+    return rc == MCB200_OK ? vals[which] : kNaN;
+}
+
+// unused bumps are 0 (their legs collapse onto the base leg and stay finite); only the requested estimator is read back
+extern "C" float mc_simd_call_price(float s, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_price(s, k, v, r, t, q, steps, n, 0u, 0);
+}
+extern "C" float mc_simd_put_price(float s, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_price(s, k, v, r, t, q, steps, n, 0u, 1);
+}
+extern "C" float mc_simd_call_price_av(float s, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_price(s, k, v, r, t, q, steps, n, MCB200_ANTITHETIC, 0);
+}
+extern "C" float mc_simd_put_price_av(float s, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_price(s, k, v, r, t, q, steps, n, MCB200_ANTITHETIC, 1);
+}
+extern "C" float mc_simd_call_delta(float s, float ds, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{ds, 0.0f, 0.0f, 0.0f}, EST_CALL_DELTA);
+}
+extern "C" float mc_simd_put_delta(float s, float ds, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{ds, 0.0f, 0.0f, 0.0f}, EST_PUT_DELTA);
+}
+extern "C" float mc_simd_gamma(float s, float ds, float k, float v, float r, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{ds, 0.0f, 0.0f, 0.0f}, EST_GAMMA);
+}
+extern "C" float mc_simd_vega(float s, float k, float v, float dv, float r, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{0.0f, dv, 0.0f, 0.0f}, EST_VEGA);
+}
+extern "C" float mc_simd_call_rho(float s, float k, float v, float r, float dr, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{0.0f, 0.0f, dr, 0.0f}, EST_CALL_RHO);
+}
+extern "C" float mc_simd_put_rho(float s, float k, float v, float r, float dr, float t, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{0.0f, 0.0f, dr, 0.0f}, EST_PUT_RHO);
+}
+extern "C" float mc_simd_call_theta(float s, float k, float v, float r, float t, float dt, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{0.0f, 0.0f, 0.0f, dt}, EST_CALL_THETA);
+}
+extern "C" float mc_simd_put_theta(float s, float k, float v, float r, float t, float dt, float q, float steps, float n) {
+    return dropin_greek(s, k, v, r, t, q, steps, n, mcb200_bumps{0.0f, 0.0f, 0.0f, dt}, EST_PUT_THETA);
+}

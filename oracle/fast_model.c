@@ -45,15 +45,16 @@ void fast_model_stream_paths(uint64_t state[4], int half_steps, int n_paths, flo
 
 /* Terminal-scale constants of the fast convention from the reference's f32 constants (mc_simd.rs:36-45):
  *   growth = exp(M * sqrt(2)*sidt + steps*nudt) = exp2(M' * c2 + d2),
- *   c2 = sqrt(2 ln 2) * sqrt(2)*sidt * log2(e),  d2 = steps*nudt * log2(e)   (folded in fp64, rounded once). */
+ *   c2 = sqrt(2)*sidt * (sqrt(2 ln 2) * log2 e),  d2 = steps*nudt * log2 e, all in f32 like the kernel prologue. */
 void fast_model_constants(float vol, float r, float q, float years, float steps, float *c2, float *d2) {
     const float dt = years / steps;
     const float nudt = (r - q - 0.5f * (vol * vol)) * dt;
     const float sidt = vol * sqrtf(dt);
     const float drift = steps * nudt;
     const float diff = 1.41421356237309504880f * sidt;
-    *c2 = (float)((double)diff * 1.17741002251547469101 /* sqrt(2 ln 2) */ * 1.44269504088896340736 /* log2 e */);
-    *d2 = (float)((double)drift * 1.44269504088896340736);
+    const float k = 1.17741002251547469101f /* sqrt(2 ln 2) */ * 1.44269504088896340736f /* log2 e */;
+    *c2 = diff * k;
+    *d2 = drift * 1.44269504088896340736f;
 }
 
 float fast_model_growth(float m, float c2, float d2) { return exp2f(fmaf(m, c2, d2)); }

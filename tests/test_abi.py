@@ -1,0 +1,139 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/mcb200.h declares, the launch
+planner (pure host logic) behaves, and the product path fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_package
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcb200_[a-z0-9_]+|mc_simd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    pkg.build()
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 30
+    for fn in ("mc_simd_call_price", "mc_simd_put_price", "mc_simd_call_price_av", "mc_simd_put_price_av",
+               "mc_simd_call_delta", "mc_simd_put_delta", "mc_simd_gamma", "mc_simd_vega", "mc_simd_call_rho",
+               "mc_simd_put_rho", "mc_simd_call_theta", "mc_simd_put_theta", "mcb200_price_batch",
+               "mcb200_greeks_batch"):
+        assert fn in names
+    for name in names:
+        assert hasattr(lib, name), "libmcb200.so does not export %s" % name
+
+
+def test_python_mirror_has_reference_api(pkg):
+    """Same twelve names and positional parameter order as src/mc_simd.rs:477-779."""
+    import inspect
+    expect = {
+        "call_price": "spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "put_price": "spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "call_price_av": "spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "put_price_av": "spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "call_delta": "spot delta_spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "put_delta": "spot delta_spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "gamma": "spot delta_spot strike volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "vega": "spot strike volatility delta_volatility risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "call_rho": "spot strike volatility risk_free_rate delta_risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "put_rho": "spot strike volatility risk_free_rate delta_risk_free_rate years_to_expiry dividend_yield steps num_trials",
+        "call_theta": "spot strike volatility risk_free_rate years_to_expiry delta_years_to_expiry dividend_yield steps num_trials",
+        "put_theta": "spot strike volatility risk_free_rate years_to_expiry delta_years_to_expiry dividend_yield steps num_trials",
+    }
+    for name, params in expect.items():
+        assert list(inspect.signature(getattr(pkg.mc_simd, name)).parameters) == params.split(), name
+
+
+def test_planner_reference_chunking(pkg):
+    """paths = 8*floor(trials/8), pairs = floor(steps)/2 (mc_simd.rs:47,49); every path is covered exactly once."""
+    for n, steps, trials, slots in [(112, 100.0, 1000.0, 1184), (112, 100.0, 20000.0, 1184), (112, 1000.0, 2000.0, 1184),
+                                    (4096, 252.0, 1e5, 1184), (100000, 252.0, 1e6, 1184), (1, 101.0, 1007.0, 1184),
+                                    (3, 7.0, 8.0, 16), (1, 252.0, 1e6, 1184), (5, 100.0, 3.0, 1184)]:
+        p = pkg.plan_query(n, steps, trials, slots)
+        assert p["n_paths"] == 8 * (int(trials) // 8)
+        assert p["half_steps"] == int(steps) // 2
+        assert p["path_steps"] == n * p["n_paths"] * 2 * p["half_steps"]
+        if p["n_paths"] == 0:
+            assert p["grid"] == 0
+            continue
+        assert p["slices"] * p["paths_per_slice"] >= p["n_paths"]
+        assert (p["slices"] - 1) * p["paths_per_slice"] < p["n_paths"]
+        assert p["paths_per_thread"] == math.ceil(p["paths_per_slice"] / 256) <= 4096
+        assert p["items"] == n * p["slices"] and p["grid"] == min(slots, p["items"])
+
+
+def test_planner_fills_the_machine(pkg):
+    """Few options / many trials must still spread over all resident CTAs; many options need one slice each."""
+    slots = 148 * 8
+    few = pkg.plan_query(1, 252.0, 1e6, slots)
+    assert few["items"] >= 0.8 * slots
+    many = pkg.plan_query(100000, 252.0, 1e4, slots)
+    assert many["slices"] == 1
+    c2 = pkg.plan_query(112, 100.0, 20000.0, slots)
+    ideal = 112 * 20000 / (slots * 256)
+    waves = math.ceil(c2["items"] / slots)
+    assert waves * c2["paths_per_thread"] <= 1.15 * ideal
+
+
+def test_planner_rejects_bad_requests(pkg):
+    for n, steps, trials in [(-1, 100.0, 1000.0), (1, 0.0, 1000.0), (1, float("nan"), 1000.0), (1, 100.0, -8.0),
+                             (1, 100.0, float("inf")), (1, 1e10, 1000.0)]:
+        with pytest.raises(pkg.Mcb200Error):
+            pkg.plan_query(n, steps, trials, 1184)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
+def test_no_cpu_fallback(pkg):
+    """Without a GPU the context cannot be created, batches raise and the drop-ins return NaN with a reason."""
+    with pytest.raises(pkg.Mcb200Error) as e:
+        pkg.Context()
+    assert e.value.status == 3
+    v = pkg.mc_simd.call_price(100.0, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 1000.0)
+    assert math.isnan(v) and "no CPU path" in pkg.mc_simd.last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "monte-carlo-options-simd_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "libcpubaseline" not in src, f
+
+
+def test_jump_table_doubling_chain(oracle):
+    """include/xoshiro256_jump_tables.h: entry k applied twice == entry k+1 applied once, starting from the published
+    JUMP polynomial (entry 0); so entry k really is jump^(2^k)."""
+    text = open(os.path.join(ROOT, "include", "xoshiro256_jump_tables.h")).read()
+    rows = re.findall(r"\{(0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL\}", text)
+    table = [[int(x, 16) for x in r] for r in rows]
+    assert table[0] == [0x180ec6d33cfd0aba, 0xd5a61266f0c9392c, 0xa9582618e03fc9aa, 0x39abdc4529b1661c]
+    assert table[-1] == [0x76e15d3efefdcbbf, 0xc5004e441c522fb3, 0x77710069854ee241, 0x39109bb02acbe635]  # LONG_JUMP
+    state = [0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9, 0x94d049bb133111eb, 0x2545f4914f6cdd1d]
+    for k in range(0, 24):
+        twice = oracle.xoshiro_apply_poly(oracle.xoshiro_apply_poly(state, table[k]), table[k])
+        once = oracle.xoshiro_apply_poly(state, table[k + 1])
+        assert list(twice) == list(once), k
+
+
+def test_sharding_partitions(pkg):
+    sh = pkg.sharding
+    for n, w in [(112, 1), (112, 2), (113, 8), (5, 8), (100000, 8)]:
+        blocks = [sh.partition_options(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+        sizes = [b[1] - b[0] for b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    for trials, w in [(20000.0, 2), (1000.0, 8), (1e6, 8), (1007.0, 3)]:
+        parts = [sh.partition_trials(trials, w, r) for r in range(w)]
+        assert all(p[0] % 8 == 0 for p in parts)
+        assert sum(p[0] for p in parts) == parts[0][1] == 8 * (int(trials) // 8)

@@ -1,0 +1,384 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of libmcb200.so and is
+checked against the CPU oracle (oracle/), the golden fixtures and the Black-Scholes closed form.
+
+Bars (BASELINE.json north_star):
+  * fixed seeds + same generator: per-path terminal prices within a stated fp32 relative tolerance
+        -> REL_TOL_PATH = 1e-4 is the contract; the MUFU-based kernels are expected (and asserted) at <= 2e-5;
+  * prices and Greeks within 3 standard errors of the reference algorithm (the oracle restatement) and of bs.rs;
+  * the reference's own tests (src/mc_simd.rs:781-907) replayed with their absolute tolerances.
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_PATH = 1e-4        # stated contract for per-path S_T (fp32, MUFU transcendentals)
+REL_TOL_PATH_TIGHT = 2e-5  # what the kernels are expected to deliver for <= 1000 steps
+GRID = dict(strike=110.0, vol=0.25, r=0.05, t=0.5, q=0.02)     # benches/benchmark.rs:10-16
+SEED = 0x5EED5EED5EED5EED
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(device=0, seed=SEED)
+    yield c
+    c.close()
+
+
+def bench_spots():
+    return np.arange(50, 162, dtype=np.float32)      # 112 spots (benches/benchmark.rs:10-11)
+
+
+# ---------------------------------------------------------------------------------------------- generator substreams
+def test_pool_states_are_jump_substreams(ctx, oracle, xoshiro_kat):
+    """Thread slot i holds jump^i(splitmix64(seed)); block b starts at long_jump^b."""
+    jump = [int(x) for x in xoshiro_kat["jump_poly"]]
+    x = np.array([SEED], np.uint64)
+    base = [int(oracle.lib().ref_splitmix64(x.ctypes.data_as(oracle._u64p))) for _ in range(4)]
+    states = ctx.export_states(0, 70)
+    s = base
+    for i in range(70):
+        assert [int(v) for v in states[i]] == [int(v) for v in s], i
+        s = oracle.xoshiro_apply_poly(s, jump)
+    # a far slot via the doubling table: 2^12 + 2^3 + 1
+    import re, os
+    from conftest import ROOT
+    rows = re.findall(r"\{(0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL\}",
+                      open(os.path.join(ROOT, "include", "xoshiro256_jump_tables.h")).read())
+    table = [[int(v, 16) for v in r] for r in rows]
+    far = base
+    for k in (0, 3, 12):
+        far = oracle.xoshiro_apply_poly(far, table[k])
+    got = ctx.export_states(4096 + 8 + 1, 1)[0]
+    assert [int(v) for v in got] == [int(v) for v in far]
+
+
+def test_substream_blocks_use_long_jump(pkg, oracle, xoshiro_kat):
+    ljump = [int(x) for x in xoshiro_kat["long_jump_poly"]]
+    with pkg.Context(device=0, seed=77, substream_block=0) as a, pkg.Context(device=0, seed=77, substream_block=2) as b:
+        s0 = [int(v) for v in a.export_states(5, 1)[0]]
+        s2 = [int(v) for v in b.export_states(5, 1)[0]]
+    want = oracle.xoshiro_apply_poly(oracle.xoshiro_apply_poly(s0, ljump), ljump)
+    assert s2 == [int(v) for v in want]
+
+
+# ---------------------------------------------------------------------------------------------- per-path parity
+@pytest.mark.parametrize("steps,trials", [(100.0, 1024.0), (1000.0, 512.0), (252.0, 2000.0), (101.0, 1007.0)])
+def test_reference_stream_per_path_parity(ctx, oracle, steps, trials):
+    """Same seeds, same generator, same draw order as the reference: every path's S_T/S agrees with the oracle."""
+    spots = np.array([80.0, 110.0, 140.0], np.float32)
+    nch = oracle.n_chunks(trials)
+    seeds = np.stack([oracle.chunk_seeds(nch, 10 + i) for i in range(len(spots))])
+    got = ctx.price_batch_refstream(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], steps, trials,
+                                    seeds, want_growth=True)
+    for i, s in enumerate(spots):
+        for mult, key in ((1.0, "call"), (-1.0, "put")):
+            ref = oracle.pricing_detail(float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], steps,
+                                        trials, mult, seeds[i], want_paths=True)
+            rel = np.abs(got["growth"][i] - ref["growth"]) / ref["growth"]
+            assert rel.max() < REL_TOL_PATH_TIGHT < REL_TOL_PATH, (s, rel.max())
+            # same paths -> same price up to fp32 rounding of sums (oracle sums in f32 like the reference)
+            assert got[key][i] == pytest.approx(ref["price"], rel=2e-4, abs=2e-4), (s, key)
+            assert got[key + "_se"][i] == pytest.approx(ref["se"], rel=1e-3, abs=1e-5)
+
+
+def test_reference_stream_antithetic_and_greeks_match_oracle(ctx, oracle):
+    s, k, v, r, t, q = 112.0, 110.0, 0.2, 0.05, 1.0, 0.02
+    steps, trials = 100.0, 4096.0
+    seeds = oracle.chunk_seeds(oracle.n_chunks(trials), 21)
+    av = ctx.price_batch_refstream([s], k, v, r, t, q, steps, trials, seeds, antithetic=True)
+    assert av["call"][0] == pytest.approx(oracle.mc("call_price_av", s, k, v, r, t, q, steps, trials, seeds=seeds), rel=2e-4)
+    assert av["put"][0] == pytest.approx(oracle.mc("put_price_av", s, k, v, r, t, q, steps, trials, seeds=seeds), rel=2e-4)
+    h = dict(delta_spot=0.5, delta_volatility=0.01, delta_risk_free_rate=0.01, delta_years_to_expiry=0.01)
+    g = ctx.greeks_batch_refstream([s], k, v, r, t, q, steps, trials, seeds, **h)
+    want = {
+        "call": oracle.mc("call_price", s, k, v, r, t, q, steps, trials, seeds=seeds),
+        "put": oracle.mc("put_price", s, k, v, r, t, q, steps, trials, seeds=seeds),
+        "call_delta": oracle.mc("call_delta", s, h["delta_spot"], k, v, r, t, q, steps, trials, seeds=seeds),
+        "put_delta": oracle.mc("put_delta", s, h["delta_spot"], k, v, r, t, q, steps, trials, seeds=seeds),
+        "gamma": oracle.mc("gamma", s, h["delta_spot"], k, v, r, t, q, steps, trials, seeds=seeds),
+        "vega": oracle.mc("vega", s, k, v, h["delta_volatility"], r, t, q, steps, trials, seeds=seeds),
+        "call_rho": oracle.mc("call_rho", s, k, v, r, h["delta_risk_free_rate"], t, q, steps, trials, seeds=seeds),
+        "put_rho": oracle.mc("put_rho", s, k, v, r, h["delta_risk_free_rate"], t, q, steps, trials, seeds=seeds),
+        "call_theta": oracle.mc("call_theta", s, k, v, r, t, h["delta_years_to_expiry"], q, steps, trials, seeds=seeds),
+        "put_theta": oracle.mc("put_theta", s, k, v, r, t, h["delta_years_to_expiry"], q, steps, trials, seeds=seeds),
+    }
+    # same paths: the only differences are fp32 rounding (the oracle differences f32 price sums like the reference,
+    # the kernel accumulates per-path differences), so agreement is far inside one standard error
+    for name, ref in want.items():
+        tol = 0.05 * float(g[name + "_se"][0]) + 2e-3 * abs(ref) + 1e-4
+        assert abs(float(g[name][0]) - ref) <= tol, (name, float(g[name][0]), ref, float(g[name + "_se"][0]))
+
+
+def test_production_stream_per_path_parity(pkg, oracle):
+    """Production convention (one 64-bit draw per Box-Muller pair, per-thread substreams): every path reproduced by
+    the CPU model from the exported generator states and the launch plan."""
+    with pkg.Context(device=0, seed=4242) as c:
+        spots = np.array([95.0, 120.0], np.float32)
+        steps, trials = 252.0, 3000.0
+        plan = c.plan(len(spots), steps, trials)
+        n_threads = plan["grid"] * 256
+        before = c.export_states(0, n_threads)
+        got = c.price_batch_dump(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], steps, trials)
+        after = c.export_states(0, n_threads)
+        c2, d2 = oracle.fast_constants(GRID["vol"], GRID["r"], GRID["q"], GRID["t"], steps)
+        worst = 0.0
+        rng = np.random.default_rng(0)
+        items = [(o, sl) for o in range(len(spots)) for sl in range(plan["slices"])]
+        assert len(items) == plan["grid"]            # one item per CTA here
+        for item in rng.choice(len(items), size=min(6, len(items)), replace=False):
+            o, sl = items[item]
+            lo = sl * plan["paths_per_slice"]
+            hi = min(lo + plan["paths_per_slice"], plan["n_paths"])
+            for t in rng.choice(256, size=12, replace=False):
+                paths = np.arange(lo + t, hi, 256)
+                slot = item * 256 + t
+                m, st = oracle.fast_stream_paths(before[slot], plan["half_steps"], len(paths))
+                assert [int(x) for x in st] == [int(x) for x in after[slot]]      # stream advanced exactly that far
+                if len(paths):
+                    want = oracle.fast_growth(m, c2, d2)
+                    rel = np.abs(got["growth"][o, paths] - want) / want
+                    worst = max(worst, float(rel.max()))
+        assert worst < REL_TOL_PATH_TIGHT < REL_TOL_PATH, worst
+        # and the reported price is the discounted mean of exactly those paths
+        for o, s in enumerate(spots):
+            pay = np.maximum(np.float64(s) * got["growth"][o].astype(np.float64) - GRID["strike"], 0.0)
+            want = pay.sum() / trials * math.exp(-GRID["r"] * GRID["t"])
+            assert got["call"][o] == pytest.approx(want, rel=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- reference tests replayed
+def _dropin(pkg, c):
+    s, k, v, r, t, q = c["params"]
+    fn, h, steps, trials = c["mc_function"], c["bump"], float(c["steps"]), float(c["trials"])
+    m = pkg.mc_simd
+    if fn in ("call_price", "put_price", "call_price_av", "put_price_av"):
+        return getattr(m, fn)(s, k, v, r, t, q, steps, trials)
+    if fn in ("call_delta", "put_delta", "gamma"):
+        return getattr(m, fn)(s, h, k, v, r, t, q, steps, trials)
+    if fn == "vega":
+        return m.vega(s, k, v, h, r, t, q, steps, trials)
+    if fn in ("call_rho", "put_rho"):
+        return getattr(m, fn)(s, k, v, r, h, t, q, steps, trials)
+    return getattr(m, fn)(s, k, v, r, t, h, q, steps, trials)
+
+
+def test_reference_tests_through_dropins(pkg, bs_cases):
+    """src/mc_simd.rs:781-907 and src/mc.rs:75-121: same parameters, same absolute tolerances, via the 12 drop-ins."""
+    pkg.mc_simd.reset_default_context(device=0, seed=2024)
+    for c in bs_cases:
+        got = _dropin(pkg, c)
+        assert not math.isnan(got), (c["reference_test"], pkg.mc_simd.last_error())
+        err = abs(got - c["bs_f32"])
+        assert (err < c["tolerance"]) if c["strict"] else (err <= c["tolerance"]), (c["reference_test"], got)
+
+
+# ---------------------------------------------------------------------------------------------- 3 SE vs closed form / oracle
+def _z(value, se, exact, floor):
+    return abs(float(value) - exact) / max(float(se), floor)
+
+
+def test_c2_prices_within_3se_of_closed_form(ctx, oracle):
+    """Config 2: call_price/put_price, 112 spots x 20000 trials x 100 steps vs the bs closed form."""
+    spots = bench_spots()
+    res = ctx.price_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 20000.0)
+    zs = []
+    for i, s in enumerate(spots):
+        for key, name in (("call", "call_price"), ("put", "put_price")):
+            exact = oracle.bs64(name, float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+            # deep out-of-the-money points can see no payoff at all (SE = 0): absolute floor of 2e-3
+            zs.append(_z(res[key][i], res[key + "_se"][i], exact, 2e-3))
+    zs = np.array(zs)
+    assert (zs > 3.0).mean() <= 0.02 and zs.max() < 4.5, (zs.max(), (zs > 3).sum())
+    assert np.sqrt((zs ** 2).mean()) < 1.3          # z-scores look like |N(0,1)|: no systematic bias
+
+
+def test_c3_antithetic_within_3se(ctx, oracle):
+    """Config 3: call_price_av/put_price_av, 112 spots x 2000 trials x 1000 steps."""
+    spots = bench_spots()
+    res = ctx.price_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 1000.0, 2000.0,
+                          antithetic=True)
+    zs = []
+    for i, s in enumerate(spots):
+        for key, name in (("call", "call_price"), ("put", "put_price")):
+            exact = oracle.bs64(name, float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+            zs.append(_z(res[key][i], res[key + "_se"][i], exact, 5e-3))
+    zs = np.array(zs)
+    assert (zs > 3.0).mean() <= 0.03 and zs.max() < 4.5, (zs.max(), (zs > 3).sum())
+
+
+def test_within_3se_of_reference_algorithm(ctx, oracle):
+    """GPU production estimator vs the oracle restatement of mc_simd on independent seeds: two independent estimators
+    of the same quantity, tolerance 3*sqrt(se_gpu^2 + se_oracle^2)."""
+    spots = np.array([90.0, 100.0, 110.0, 120.0, 140.0], np.float32)
+    res = ctx.price_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 20000.0)
+    for i, s in enumerate(spots):
+        seeds = oracle.chunk_seeds(2500, 300 + i)
+        for mult, key in ((1.0, "call"), (-1.0, "put")):
+            ref = oracle.pricing_detail(float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0,
+                                        20000.0, mult, seeds)
+            tol = 3.0 * math.sqrt(float(res[key + "_se"][i]) ** 2 + ref["se"] ** 2) + 1e-3
+            assert abs(float(res[key][i]) - ref["mean"]) <= tol, (s, key, float(res[key][i]), ref["mean"], tol)
+            # the SE itself is an estimate of the same payoff dispersion
+            assert float(res[key + "_se"][i]) == pytest.approx(ref["se"], rel=0.15, abs=2e-3)
+
+
+def test_c4_greeks_within_3se_of_closed_form(ctx, oracle):
+    """Config 4 (reduced option count): all Greeks from one pass, 64 spots x 1e5 trials x 252 steps."""
+    spots = (50.0 + 112.0 * np.arange(0, 4096, 64) / 4096.0).astype(np.float32)
+    h = dict(delta_spot=0.01, delta_volatility=0.01, delta_risk_free_rate=0.01, delta_years_to_expiry=0.001)
+    g = ctx.greeks_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 252.0, 1e5, **h)
+    names = {"call": "call_price", "put": "put_price", "call_delta": "call_delta", "put_delta": "put_delta",
+             "gamma": "gamma", "vega": "vega", "call_rho": "call_rho", "put_rho": "put_rho",
+             "call_theta": "call_theta", "put_theta": "put_theta"}
+    floors = {"call": 2e-3, "put": 2e-3, "call_delta": 2e-4, "put_delta": 2e-4, "gamma": 5e-4, "vega": 2e-4,
+              "call_rho": 2e-4, "put_rho": 2e-4, "call_theta": 5e-3, "put_theta": 5e-3}
+    for key, bsname in names.items():
+        zs = []
+        for i, s in enumerate(spots):
+            exact = oracle.bs64(bsname, float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+            # central differences carry an O(h^2) bias; it is far below the floors at these bumps
+            zs.append(_z(g[key][i], g[key + "_se"][i], exact, floors[key]))
+        zs = np.array(zs)
+        assert (zs > 3.0).mean() <= 0.05 and zs.max() < 4.5, (key, zs.max(), (zs > 3).sum())
+    # put-call parity of the deltas holds path by path: call_delta - put_delta = E[g0] e^{-rT} ~ e^{-qT}
+    assert np.allclose(g["call_delta"] - g["put_delta"], math.exp(-GRID["q"] * GRID["t"]), atol=5e-3)
+
+
+# ---------------------------------------------------------------------------------------------- determinism, edges
+def test_bitwise_reproducible_and_streams_advance(pkg):
+    spots = bench_spots()
+    args = (spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 1000.0)
+    with pkg.Context(device=0, seed=9) as a:
+        r1 = a.price_batch(*args)
+        r2 = a.price_batch(*args)          # continues the substreams: fresh paths
+        a.set_seed(9)
+        r3 = a.price_batch(*args)
+    with pkg.Context(device=0, seed=9) as b:
+        r4 = b.price_batch(*args)
+    with pkg.Context(device=0, seed=9, substream_block=1) as c:
+        r5 = c.price_batch(*args)
+    assert np.array_equal(r1["call"], r3["call"]) and np.array_equal(r1["call"], r4["call"])
+    assert np.array_equal(r1["put_se"], r4["put_se"])
+    assert not np.array_equal(r1["call"], r2["call"])
+    assert not np.array_equal(r1["call"], r5["call"])
+
+
+def test_options_get_independent_paths(ctx):
+    """Identical options in one batch must not share paths (the reference draws fresh paths per call)."""
+    res = ctx.price_batch(np.full(8, 110.0, np.float32), 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 1000.0)
+    assert len(set(res["call"].tolist())) == 8
+
+
+def test_reference_quirks_on_gpu(ctx, oracle):
+    """num_trials not a multiple of 8 and odd steps behave like the reference (mc_simd.rs:44-49,77)."""
+    seeds = oracle.chunk_seeds(125, 3)
+    a = ctx.price_batch_refstream([120.0], 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, 1000.0, seeds)
+    b = ctx.price_batch_refstream([120.0], 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, 1007.0, seeds)
+    assert b["call"][0] == pytest.approx(a["call"][0] * 1000.0 / 1007.0, rel=1e-6)
+    e = ctx.price_batch_refstream([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, 4.0, 64.0, seeds[:8], want_growth=True)
+    o = ctx.price_batch_refstream([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, 5.0, 64.0, seeds[:8], want_growth=True)
+    # same normals (4), but dt and the drift term use steps = 5
+    c_e = oracle.pricing_detail(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 4.0, 64.0, 1.0, seeds[:8], want_paths=True)
+    c_o = oracle.pricing_detail(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 5.0, 64.0, 1.0, seeds[:8], want_paths=True)
+    assert np.allclose(e["growth"][0], c_e["growth"], rtol=REL_TOL_PATH_TIGHT)
+    assert np.allclose(o["growth"][0], c_o["growth"], rtol=REL_TOL_PATH_TIGHT)
+
+
+def test_empty_and_degenerate_inputs(pkg, ctx):
+    empty = ctx.price_batch(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32),
+                            np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32), 100.0, 1000.0)
+    assert empty["call"].size == 0
+    # fewer than 8 trials: zero chunks, the reference returns 0/num_trials * disc = 0
+    z = ctx.price_batch([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, 5.0)
+    assert z["call"][0] == 0.0 and z["put"][0] == 0.0 and z["call_se"][0] == 0.0
+    # steps = 1: no normals at all, deterministic forward
+    d = ctx.price_batch([100.0], 90.0, 0.2, 0.05, 1.0, 0.0, 1.0, 64.0)
+    fwd = 100.0 * math.exp(0.05 - 0.5 * 0.04) - 90.0
+    assert d["call"][0] == pytest.approx(fwd * math.exp(-0.05), rel=1e-5)
+    assert d["call_se"][0] <= 2e-3 * d["call"][0]      # fp32 sum of squares: variance resolved to ~1e-7 * mean^2
+    for bad in [dict(steps=0.0, num_trials=1000.0), dict(steps=float("nan"), num_trials=1000.0),
+                dict(steps=100.0, num_trials=-1.0)]:
+        with pytest.raises(pkg.Mcb200Error):
+            ctx.price_batch([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, bad["steps"], bad["num_trials"])
+    assert math.isnan(pkg.mc_simd.call_price(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 0.0, 1000.0))
+    assert "invalid request" in pkg.mc_simd.last_error()
+
+
+def test_large_batch_many_slices_and_waves(ctx, oracle):
+    """More work items than resident CTAs (persistent loop) and a many-slice single option (second pass)."""
+    spots = (80.0 + 60.0 * np.arange(3000) / 3000.0).astype(np.float32)
+    res = ctx.price_batch(spots, 110.0, 0.25, 0.05, 0.5, 0.02, 20.0, 512.0)
+    exact = np.array([oracle.bs64("call_price", float(s), 110.0, 0.25, 0.05, 0.5, 0.02) for s in spots])
+    z = np.abs(res["call"] - exact) / np.maximum(res["call_se"], 2e-2)
+    assert (z > 3.0).mean() < 0.02 and z.max() < 5.0
+    one = ctx.price_batch([110.0], 110.0, 0.25, 0.05, 0.5, 0.02, 50.0, 2_000_000.0)
+    ex = oracle.bs64("call_price", 110.0, 110.0, 0.25, 0.05, 0.5, 0.02)
+    assert abs(one["call"][0] - ex) <= 3.5 * one["call_se"][0] + 1e-3
+    assert 0.007 < one["call_se"][0] < 0.011            # payoff std ~12.7 at the money / sqrt(2e6)
+
+
+def test_device_resident_and_moment_paths_agree(pkg):
+    """mcb200_price_batch_device == mcb200_price_moments_device + mcb200_price_finalize_device on the same streams."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    spots = torch.arange(50, 162, dtype=torch.float32, device=dev)
+    n = spots.numel()
+    cols = [spots] + [torch.full((n,), v, dtype=torch.float32, device=dev) for v in
+                      (GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])]
+    ptrs = [c.data_ptr() for c in cols]
+    out = torch.zeros(4, n, dtype=torch.float32, device=dev)
+    out2 = torch.zeros(4, n, dtype=torch.float32, device=dev)
+    mom = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    stream = ts.cuda_stream
+    with pkg.Context(device=0, seed=5) as a:
+        a.price_batch_device(n, ptrs, 100.0, 20000.0, [out[i].data_ptr() for i in range(4)], stream=stream)
+        torch.cuda.synchronize()
+        a.set_seed(5)
+        a.price_moments_device(n, ptrs, 100.0, 20000.0, mom.data_ptr(), stream=stream)
+        a.price_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), mom.data_ptr(), 20000.0, 20000.0,
+                                [out2[i].data_ptr() for i in range(4)], stream=stream)
+        torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    host = pkg.sharding.finalize_price_moments(mom.cpu().numpy(), cols[3].cpu().numpy(), cols[4].cpu().numpy(), 20000.0,
+                                               20000.0)
+    assert np.allclose(host["call"], out[0].cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(host["put_se"], out[3].cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_trials_sharded_over_substream_blocks(pkg, oracle):
+    """Trials-minor sharding emulated on one GPU: two contexts on different long_jump blocks each simulate half of
+    the trials; summed moments finalise to an estimate with the full-sample standard error."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    spots = torch.tensor([100.0, 110.0, 120.0], dtype=torch.float32, device=dev)
+    n = spots.numel()
+    cols = [spots] + [torch.full((n,), v, dtype=torch.float32, device=dev) for v in
+                      (GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])]
+    ptrs = [c.data_ptr() for c in cols]
+    total = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    stream = ts.cuda_stream
+    trials = 80000.0
+    for rank in range(2):
+        local, total_paths = pkg.sharding.partition_trials(trials, 2, rank)
+        m = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+        with pkg.Context(device=0, seed=31, substream_block=rank) as c:
+            c.price_moments_device(n, ptrs, 100.0, float(local), m.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+        total += m
+    out = torch.zeros(4, n, dtype=torch.float32, device=dev)
+    with pkg.Context(device=0, seed=31) as c:
+        c.price_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), total.data_ptr(), float(total_paths), trials,
+                                [out[i].data_ptr() for i in range(4)], stream=stream)
+        torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i, s in enumerate((100.0, 110.0, 120.0)):
+        exact = oracle.bs64("call_price", s, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+        assert abs(out[0, i] - exact) <= 3.5 * out[2, i]
+        assert out[2, i] < 0.08        # ~ sigma_payoff / sqrt(80000)
