@@ -15,14 +15,17 @@
 namespace mcb200 {
 
 constexpr int kChains = 8;
-constexpr int kIters = 2048;
+constexpr int kIters = 8192;
 
 enum PipeOp { OP_MUFU_LG2, OP_MUFU_SIN, OP_MUFU_SQRT, OP_MUFU_EX2, OP_FFMA, OP_FADD, OP_FMUL, OP_LOP3, OP_SHF,
-              OP_IADD3, OP_IADD_CARRY, OP_IMAD, OP_IMAD_SHL, OP_MIX_PAIR, OP_XOSHIRO, OP_COUNT };
+              OP_IADD3, OP_IADD_CARRY, OP_IMAD, OP_IMAD_HI, OP_IMAD_WIDE,
+              OP_PAIR_V0, OP_PAIR_V1, OP_PAIR_V0H, OP_PAIR_V1H, OP_XOSHIRO_V0, OP_XOSHIRO_V1, OP_COUNT };
 
-static const char* kOpNames[OP_COUNT] = {"mufu_lg2", "mufu_sin", "mufu_sqrt", "mufu_ex2", "ffma", "fadd", "fmul",
-                                         "lop3", "shf_funnel", "iadd3", "iadd64_carry", "imad", "imad_shl",
-                                         "pair_fast_loop", "xoshiro256pp_next"};
+static const char* kOpNames[OP_COUNT] = {"mufu_lg2", "mufu_sin(+fmul)", "mufu_sqrt", "mufu_ex2", "ffma", "fadd", "fmul",
+                                         "lop3", "shf_funnel", "iadd3_3in", "iadd64_carry_pair", "imad", "imad_hi",
+                                         "imad_wide",
+                                         "pair_v0", "pair_v1_twide", "pair_v0_madhi", "pair_v1_twide_madhi",
+                                         "xoshiro_v0", "xoshiro_v1_twide"};
 
 template <int OP>
 __device__ __forceinline__ void op_step(uint32_t& x, uint32_t y, uint32_t z) {
@@ -38,9 +41,9 @@ __device__ __forceinline__ void op_step(uint32_t& x, uint32_t y, uint32_t z) {
     if (OP <= OP_FMUL) x = __float_as_uint(fx);
     if (OP == OP_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(z));
     if (OP == OP_SHF) asm volatile("shf.l.wrap.b32 %0, %0, %1, 13;" : "+r"(x) : "r"(y));
-    if (OP == OP_IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
+    if (OP == OP_IADD3) asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(x) : "r"(y), "r"(z));
     if (OP == OP_IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
-    if (OP == OP_IMAD_SHL) asm volatile("shl.b32 %0, %0, 3;" : "+r"(x));
+    if (OP == OP_IMAD_HI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
 }
 
 template <int OP>
@@ -51,16 +54,31 @@ __global__ void __launch_bounds__(kThreads) pipe_kernel(uint32_t* sink, long lon
     const uint32_t y = 0x3f800001u + (seed & 7u), z = 0x3a000000u + (seed & 3u);
     __syncthreads();
     const long long t0 = clock64();
-    if (OP == OP_MIX_PAIR || OP == OP_XOSHIRO) {
+    if (OP >= OP_PAIR_V0) {
         Xoshiro256 g{v[0], v[1], v[2], v[3], v[4] | 1u, v[5], v[6], v[7]};
         float acc = 0.0f;
         uint32_t mix = 0;
+        const uint32_t two23 = (seed >> 1 | 1u) << 23;      // 2^23, known only at run time (seed = 1, 2)
 #pragma unroll 4
-        for (int i = 0; i < kIters * kChains; ++i) {
-            if (OP == OP_MIX_PAIR) acc = pair_fast(g, acc);
-            else { uint32_t hi, lo; xoshiro_next(g, hi, lo); mix ^= hi + lo; }
+        for (int i = 0; i < kIters * kChains / 8; ++i) {
+            if (OP == OP_PAIR_V0) acc = pair_fast_v<0, false>(g, acc, two23);
+            if (OP == OP_PAIR_V1) acc = pair_fast_v<1, false>(g, acc, two23);
+            if (OP == OP_PAIR_V0H) acc = pair_fast_v<0, true>(g, acc, two23);
+            if (OP == OP_PAIR_V1H) acc = pair_fast_v<1, true>(g, acc, two23);
+            if (OP == OP_XOSHIRO_V0) { uint32_t hi, lo; xoshiro_next_v<0>(g, hi, lo); mix ^= hi + lo; }
+            if (OP == OP_XOSHIRO_V1) { uint32_t hi, lo; xoshiro_next_v<1>(g, hi, lo); mix ^= hi + lo; }
         }
         v[0] = __float_as_uint(acc) ^ mix ^ g.s0l;
+    } else if (OP == OP_IMAD_WIDE) {
+        unsigned long long w[kChains];
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) w[c] = ((unsigned long long)v[c] << 32) | y;
+        for (int i = 0; i < kIters; ++i) {
+#pragma unroll
+            for (int c = 0; c < kChains; ++c) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(y), "r"(seed));
+        }
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) v[c] = (uint32_t)w[c] ^ (uint32_t)(w[c] >> 32);
     } else if (OP == OP_IADD_CARRY) {
         uint32_t lo[kChains / 2], hi[kChains / 2];
 #pragma unroll
@@ -104,12 +122,17 @@ static int run_one(cudaStream_t st, int sm_count, int ctas_per_sm, uint32_t* d_s
     double mean_cycles = 0.0; long long max_cycles = 0;
     for (int i = 0; i < grid; ++i) { mean_cycles += (double)h_cycles[i]; if (h_cycles[i] > max_cycles) max_cycles = h_cycles[i]; }
     mean_cycles /= grid;
-    // ops per thread: kIters*kChains single instructions (a 64-bit carry add counts as 2; MIX/XOSHIRO count calls)
-    const double ops_per_thread = (double)kIters * kChains;
+    // ops per thread: kIters*kChains single instructions (iadd64_carry_pair: pairs, i.e. half as many; pair_* and
+    // xoshiro_*: calls, kIters*kChains/8 of them).  Rate = thread-ops per SM / cycles of the longest-running CTA (warps
+    // finish at different times under the greedy scheduler, so the mean CTA time would overstate the rate).
+    double ops_per_thread = (double)kIters * kChains;
+    if (OP >= OP_PAIR_V0) ops_per_thread /= 8.0;
+    if (OP == OP_IADD_CARRY) ops_per_thread /= 2.0;
     const double ops_per_sm = ops_per_thread * kThreads * ctas_per_sm;
     std::memset(out, 0, sizeof(*out));
     std::snprintf(out->name, sizeof(out->name), "%s", kOpNames[OP]);
-    out->ops_per_clk_per_sm = ops_per_sm / mean_cycles;
+    out->ops_per_clk_per_sm = ops_per_sm / (double)max_cycles;
+    (void)mean_cycles;
     out->elapsed_ms = ms;
     out->sm_clock_mhz = (double)max_cycles / (ms * 1e3);
     return 0;
@@ -126,8 +149,10 @@ int run_microbench(cudaStream_t st, int sm_count, mcb200_pipe_rate* out, int cap
 #define MCB_RUN(OP) if (rc == 0 && n < cap) { rc = run_one<OP>(st, sm_count, ctas_per_sm, d_sink, d_cycles, h, &out[n]); if (rc == 0) ++n; }
     MCB_RUN(OP_MUFU_LG2) MCB_RUN(OP_MUFU_SIN) MCB_RUN(OP_MUFU_SQRT) MCB_RUN(OP_MUFU_EX2)
     MCB_RUN(OP_FFMA) MCB_RUN(OP_FADD) MCB_RUN(OP_FMUL)
-    MCB_RUN(OP_LOP3) MCB_RUN(OP_SHF) MCB_RUN(OP_IADD3) MCB_RUN(OP_IADD_CARRY) MCB_RUN(OP_IMAD) MCB_RUN(OP_IMAD_SHL)
-    MCB_RUN(OP_MIX_PAIR) MCB_RUN(OP_XOSHIRO)
+    MCB_RUN(OP_LOP3) MCB_RUN(OP_SHF) MCB_RUN(OP_IADD3) MCB_RUN(OP_IADD_CARRY) MCB_RUN(OP_IMAD) MCB_RUN(OP_IMAD_HI)
+    MCB_RUN(OP_IMAD_WIDE)
+    MCB_RUN(OP_PAIR_V0) MCB_RUN(OP_PAIR_V1) MCB_RUN(OP_PAIR_V0H) MCB_RUN(OP_PAIR_V1H)
+    MCB_RUN(OP_XOSHIRO_V0) MCB_RUN(OP_XOSHIRO_V1)
 #undef MCB_RUN
     cudaFree(d_sink); cudaFree(d_cycles);
     return rc == 0 ? n : -1;

@@ -28,15 +28,32 @@ constexpr float kSqrt2Ln2 = 1.17741002251547469101f;   // sqrt(2 ln 2)
 // Production pair update: ONE generator output -> one Box-Muller pair -> two time steps.
 //   sqrt(-ln u1) * (sin t + cos t) == sqrt(2 ln 2) * sqrt(-log2 u1) * sin(t + pi/4);  the constant is folded into the
 //   terminal scale, so the loop body is 3 MUFU (LG2, SQRT, SIN) + 4 FP32 + 2 bit-casts + the generator.
-__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc) {
+// FLOAT_MADHI builds the [1,2) floats with IMAD.HI ((x * 2^23) >> 32 + 0x3f800000) on the FMA-heavy pipe instead of
+// LEA.HI on the ALU pipe; the multiplier 2^23 must arrive at run time (two23), or ptxas folds it back into LEA.HI.
+template <int V, bool FLOAT_MADHI>
+__device__ __forceinline__ float pair_fast_v(Xoshiro256& g, float acc, uint32_t two23 = 8388608u) {
     uint32_t hi, lo;
-    xoshiro_next(g, hi, lo);
-    const float f1 = __uint_as_float((hi >> 9) | 0x3f800000u);     // [1,2)
-    const float f2 = __uint_as_float((lo >> 9) | 0x3f800000u);     // [1,2) == one full turn
+    xoshiro_next_v<V>(g, hi, lo);
+    uint32_t b1, b2;
+    if (FLOAT_MADHI) {
+        asm("mad.hi.u32 %0, %1, %2, 1065353216;" : "=r"(b1) : "r"(hi), "r"(two23));
+        asm("mad.hi.u32 %0, %1, %2, 1065353216;" : "=r"(b2) : "r"(lo), "r"(two23));
+    } else {
+        b1 = (hi >> 9) | 0x3f800000u;
+        b2 = (lo >> 9) | 0x3f800000u;
+    }
+    const float f1 = __uint_as_float(b1);                           // [1,2)
+    const float f2 = __uint_as_float(b2);                           // [1,2) == one full turn
     const float u1 = 2.0f - f1;                                     // (0,1], exact
     const float rad = mufu_sqrt(fabsf(mufu_lg2(u1)));
     const float ang = fmaf(f2, kTwoPi, kQuarterPi);
     return fmaf(rad, mufu_sin(ang), acc);
+}
+
+constexpr bool kFloatMadHi = false;  // production choice
+
+__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc, uint32_t two23 = 8388608u) {
+    return pair_fast_v<kXoVariant, kFloatMadHi>(g, acc, two23);
 }
 
 // Reference-stream pair update: consumes the generator exactly like rand32x8.rs:5-21 + mc_simd.rs:9-21

@@ -20,20 +20,38 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
+// Pipe-balance variants of the generator step.  The SM has three relevant issue targets per sub-partition: the ALU pipe
+// (LOP3 / SHF / IADD3 / LEA, 16 lanes), the FMA-heavy pipe (IMAD*, 16 lanes) and the XU pipe (MUFU, 4 lanes).  The
+// straightforward step is ALU-bound (measured, profiles/microbench_*.json), so XO_T_WIDE moves the s1 << 17 shift onto
+// IMAD.  (Moving the 64-bit adds to IMAD.WIDE was tried: ptxas splits them back into IADD3 + IMAD.X.)  All variants
+// compute bit-identical results.
+enum XoVariant : int {
+    XO_T_WIDE = 1,     // t = s1 << 17 as IMAD.WIDE.U32 (s1.lo * 2^17) + IMAD (s1.hi * 2^17 + hi) instead of SHL + SHF
+};
+
+__device__ __forceinline__ void add64(uint32_t al, uint32_t ah, uint32_t bl, uint32_t bh, uint32_t& rl, uint32_t& rh) {
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(rl), "=r"(rh) : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+}
+
 // Advance the linear engine one step and return the ++-scrambled 64-bit output as (hi, lo).
-__device__ __forceinline__ void xoshiro_next(Xoshiro256& g, uint32_t& out_hi, uint32_t& out_lo) {
+template <int V>
+__device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, uint32_t& out_lo) {
     // a = s0 + s3
     uint32_t al, ah;
-    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
-        : "=r"(al), "=r"(ah) : "r"(g.s0l), "r"(g.s0h), "r"(g.s3l), "r"(g.s3h));
+    add64(g.s0l, g.s0h, g.s3l, g.s3h, al, ah);
     // r = rotl(a, 23) + s0
     const uint32_t rh = __funnelshift_l(al, ah, 23);
     const uint32_t rl = __funnelshift_l(ah, al, 23);
-    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
-        : "=r"(out_lo), "=r"(out_hi) : "r"(rl), "r"(rh), "r"(g.s0l), "r"(g.s0h));
+    add64(g.s0l, g.s0h, rl, rh, out_lo, out_hi);
     // t = s1 << 17
-    const uint32_t tl = g.s1l << 17;
-    const uint32_t th = __funnelshift_l(g.s1l, g.s1h, 17);
+    uint32_t tl, th;
+    if (V & XO_T_WIDE) {
+        asm("{\n\t.reg .b64 w;\n\tmul.wide.u32 w, %2, 131072;\n\tmov.b64 {%0, %1}, w;\n\t}" : "=r"(tl), "=r"(th) : "r"(g.s1l));
+        asm("mad.lo.u32 %0, %1, 131072, %0;" : "+r"(th) : "r"(g.s1h));
+    } else {
+        tl = g.s1l << 17;
+        th = __funnelshift_l(g.s1l, g.s1h, 17);
+    }
     // s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = rotl(s3, 45)   (fused into 3-input XORs)
     const uint32_t x3l = g.s3l ^ g.s1l, x3h = g.s3h ^ g.s1h;        // s3 ^ s1
     const uint32_t n1l = xor3(g.s1l, g.s2l, g.s0l), n1h = xor3(g.s1h, g.s2h, g.s0h);
@@ -44,6 +62,12 @@ __device__ __forceinline__ void xoshiro_next(Xoshiro256& g, uint32_t& out_hi, ui
     // rotl(x3, 45) = rotl(swap halves, 13)
     g.s3h = __funnelshift_l(x3h, x3l, 13);
     g.s3l = __funnelshift_l(x3l, x3h, 13);
+}
+
+constexpr int kXoVariant = 0;      // production choice (see profiles/ for the measurements behind it)
+
+__device__ __forceinline__ void xoshiro_next(Xoshiro256& g, uint32_t& out_hi, uint32_t& out_lo) {
+    xoshiro_next_v<kXoVariant>(g, out_hi, out_lo);
 }
 
 __device__ __forceinline__ void xoshiro_load(Xoshiro256& g, const uint64_t* __restrict__ p) {

@@ -50,6 +50,8 @@ def lib():
         L.ref_xoshiro_outputs.argtypes = [_u64p, C.c_int, _u64p]
         L.ref_xoshiro_apply_poly.restype = None
         L.ref_xoshiro_apply_poly.argtypes = [_u64p, _u64p]
+        L.ref_splitmix64.restype = C.c_uint64
+        L.ref_splitmix64.argtypes = [_u64p]
         L.fast_model_stream_paths.restype = None
         L.fast_model_stream_paths.argtypes = [_u64p, C.c_int, C.c_int, _fp]
         L.fast_model_constants.restype = None
