@@ -246,7 +246,7 @@ static int run_moments(mcb200_ctx* c, const Request& rq, double* moments_out, cu
     SimArgs a{};
     a.opt = rq.opt; a.n_options = rq.n; a.n_paths = pl.n_paths; a.half_steps = pl.half_steps; a.steps = rq.steps;
     a.slices = pl.slices; a.paths_per_slice = pl.paths_per_slice; a.bumps = rq.bumps; a.pool = c->pool;
-    a.chunk_seeds = rq.chunk_seeds; a.partials = c->partials; a.growth_out = rq.growth_out;
+    a.chunk_seeds = rq.chunk_seeds; a.partials = c->partials; a.growth_out = rq.growth_out; a.one = 1u;
     const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     switch (key) {

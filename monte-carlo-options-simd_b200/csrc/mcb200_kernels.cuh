@@ -48,6 +48,7 @@ struct SimArgs {
     const uint64_t* chunk_seeds;   // STREAM_REF: n_options * n_paths/8 seeds of 32 x u64 (simd_rand layout)
     double* partials;      // [n_options * slices][2 * kEst]
     float* growth_out;     // DUMP only: [n_options][n_paths] terminal growth factors S_T / spot
+    uint32_t one;          // the value 1, delivered at run time so ptxas keeps IMAD.WIDE adds (mcb200_rng.cuh)
 };
 
 // f32 constants exactly as the reference computes them (mc_simd.rs:36-45), then rescaled to base-2 exponent units.
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) simulate_kernel(const SimA
     __shared__ double s_warp[kWarps][kAcc];
 
     const int t = threadIdx.x;
+    const uint32_t one = a.one;
     Xoshiro256 g;
     if (STREAM == STREAM_FAST) xoshiro_load(g, a.pool + 4ull * ((size_t)blockIdx.x * kThreads + t));
 
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) simulate_kernel(const SimA
             float m = 0.0f;
             if (STREAM == STREAM_FAST) {
 #pragma unroll 4
-                for (int i = 0; i < a.half_steps; ++i) m = pair_fast(g, m);
+                for (int i = 0; i < a.half_steps; ++i) m = pair_fast(g, m, one);
             } else {
 #pragma unroll 2
                 for (int i = 0; i < a.half_steps; ++i) m = pair_ref(g, m);

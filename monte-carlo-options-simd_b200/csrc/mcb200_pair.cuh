@@ -28,16 +28,39 @@ constexpr float kSqrt2Ln2 = 1.17741002251547469101f;   // sqrt(2 ln 2)
 // Production pair update: ONE generator output -> one Box-Muller pair -> two time steps.
 //   sqrt(-ln u1) * (sin t + cos t) == sqrt(2 ln 2) * sqrt(-log2 u1) * sin(t + pi/4);  the constant is folded into the
 //   terminal scale, so the loop body is 3 MUFU (LG2, SQRT, SIN) + 4 FP32 + 2 bit-casts + the generator.
-// FLOAT_MADHI builds the [1,2) floats with IMAD.HI ((x * 2^23) >> 32 + 0x3f800000) on the FMA-heavy pipe instead of
-// LEA.HI on the ALU pipe; the multiplier 2^23 must arrive at run time (two23), or ptxas folds it back into LEA.HI.
-template <int V, bool FLOAT_MADHI>
-__device__ __forceinline__ float pair_fast_v(Xoshiro256& g, float acc, uint32_t two23 = 8388608u) {
+// FMODE selects how the two [1,2) floats are built from the generator output (bit-identical results):
+//   0: LEA.HI  ((x >> 9) | 0x3f800000) on the ALU pipe
+//   1: IMAD.HI ((x * 2^23) >> 32 + 0x3f800000) on the FMA-heavy pipe at half rate
+//   2: IMAD.WIDE (x * 2^23 + (0x3f800000 << 32), upper word) on the FMA-heavy pipe at full rate
+//   3: IMAD.WIDE upper word k = x >> 9 read as an fp32 DENORMAL (value k * 2^-149) and rescaled by the FMA pipe, which
+//      handles denormal inputs at full rate: u1 = fma(d, -2^126, 1) = 1 - k 2^-23 (the same value as 2 - f1, exactly)
+//      and angle = fma(d, 2 pi 2^126, pi/4) -- the same angle minus one full turn.  No ALU-pipe instruction at all.
+//   4: I2FP.F32.U32.RZ of the whole 32-bit word (24 significant bits, truncated): u1 = fma(f, -2^-32, 1) in
+//      [2^-24, 1], angle = fma(f, 2 pi 2^-32, pi/4).  A different (finer) uniform grid than modes 0-3.
+// For 1 and 2 the multiplier 2^23 must arrive at run time (two23), or ptxas folds it back into LEA.HI.
+template <int V, int FMODE>
+__device__ __forceinline__ float pair_fast_v(Xoshiro256& g, float acc, uint32_t two23 = 8388608u, uint32_t one = 1u) {
     uint32_t hi, lo;
-    xoshiro_next_v<V>(g, hi, lo);
+    xoshiro_next_v<V>(g, hi, lo, one);
     uint32_t b1, b2;
-    if (FLOAT_MADHI) {
+    if (FMODE == 1) {
         asm("mad.hi.u32 %0, %1, %2, 1065353216;" : "=r"(b1) : "r"(hi), "r"(two23));
         asm("mad.hi.u32 %0, %1, %2, 1065353216;" : "=r"(b2) : "r"(lo), "r"(two23));
+    } else if (FMODE == 2) {
+        uint32_t dump;
+        unpack64(mad_wide(hi, two23, 0x3f80000000000000ull), dump, b1);
+        unpack64(mad_wide(lo, two23, 0x3f80000000000000ull), dump, b2);
+    } else if (FMODE == 3) {
+        uint32_t dump;
+        unpack64(mad_wide(hi, two23, 0ull), dump, b1);
+        unpack64(mad_wide(lo, two23, 0ull), dump, b2);
+        const float u1 = fmaf(__uint_as_float(b1), -8.507059173023462e37f, 1.0f);                    // 2^126
+        const float ang = fmaf(__uint_as_float(b2), 6.28318530717958647692f * 8.507059173023462e37f, kQuarterPi);
+        return fmaf(mufu_sqrt(fabsf(mufu_lg2(u1))), mufu_sin(ang), acc);
+    } else if (FMODE == 4) {
+        const float u1 = fmaf(__uint2float_rz(hi), -2.3283064365386963e-10f, 1.0f);                  // 2^-32
+        const float ang = fmaf(__uint2float_rz(lo), 6.28318530717958647692f * 2.3283064365386963e-10f, kQuarterPi);
+        return fmaf(mufu_sqrt(fabsf(mufu_lg2(u1))), mufu_sin(ang), acc);
     } else {
         b1 = (hi >> 9) | 0x3f800000u;
         b2 = (lo >> 9) | 0x3f800000u;
@@ -50,10 +73,10 @@ __device__ __forceinline__ float pair_fast_v(Xoshiro256& g, float acc, uint32_t 
     return fmaf(rad, mufu_sin(ang), acc);
 }
 
-constexpr bool kFloatMadHi = false;  // production choice
+constexpr int kFloatMode = 0;  // production choice
 
-__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc, uint32_t two23 = 8388608u) {
-    return pair_fast_v<kXoVariant, kFloatMadHi>(g, acc, two23);
+__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc, uint32_t one) {
+    return pair_fast_v<kXoVariant, kFloatMode>(g, acc, one << 23, one);
 }
 
 // Reference-stream pair update: consumes the generator exactly like rand32x8.rs:5-21 + mc_simd.rs:9-21

@@ -20,34 +20,76 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
-// Pipe-balance variants of the generator step.  The SM has three relevant issue targets per sub-partition: the ALU pipe
-// (LOP3 / SHF / IADD3 / LEA, 16 lanes), the FMA-heavy pipe (IMAD*, 16 lanes) and the XU pipe (MUFU, 4 lanes).  The
-// straightforward step is ALU-bound (measured, profiles/microbench_*.json), so XO_T_WIDE moves the s1 << 17 shift onto
-// IMAD.  (Moving the 64-bit adds to IMAD.WIDE was tried: ptxas splits them back into IADD3 + IMAD.X.)  All variants
-// compute bit-identical results.
+// Pipe-balance variants of the generator step.  Per SM sub-partition the relevant issue targets are the ALU pipe
+// (LOP3 / SHF / IADD3 / LEA: 16 lanes, measured 64 thread-ops/clk/SM), the FMA-heavy pipe (IMAD*: also 64/clk/SM),
+// the FMA-lite pipe (FFMA/FADD/FMUL share 128/clk/SM with the heavy one) and the XU pipe (MUFU, 16/clk/SM).  The
+// straightforward step puts 15 of its 18 instructions on the ALU pipe, which then binds the whole path kernel
+// (profiles/r1_microbench.json), so the variants below move 64-bit adds, shifts and rotates onto IMAD.WIDE / IMAD
+// (FMA-heavy) without changing the instruction count.  All variants compute bit-identical results; `one` must be the
+// value 1 delivered at run time (a kernel parameter), otherwise ptxas folds the multiply back into IADD3.
 enum XoVariant : int {
-    XO_T_WIDE = 1,     // t = s1 << 17 as IMAD.WIDE.U32 (s1.lo * 2^17) + IMAD (s1.hi * 2^17 + hi) instead of SHL + SHF
+    XO_T_WIDE = 1,      // t = s1 << 17          : IMAD.WIDE(s1.lo, 2^17) + IMAD(s1.hi, 2^17, hi)        (was IMAD.SHL + SHF)
+    XO_ADD_WIDE = 2,    // a = s0 + s3           : IMAD.WIDE(s3.lo, one, s0) + IMAD(s3.hi, one, hi)       (was IADD3 + IMAD.X)
+    XO_ROT_WIDE = 4,    // r = rotl(a, 23) + s0  : IMAD.WIDE(a.lo, 2^23, s0) + IMAD(a.hi, 2^23, hi) + SHF.R + IMAD.WIDE(a.hi >> 9, one, .)
+                        //                                                                        (was 2 SHF + IADD3 + IMAD.X)
+    XO_ROT45_WIDE = 8,  // s3 = rotl(s3 ^ s1, 45): IMAD.WIDE + IMAD + IMAD.HI                              (was 2 SHF)
 };
 
 __device__ __forceinline__ void add64(uint32_t al, uint32_t ah, uint32_t bl, uint32_t bh, uint32_t& rl, uint32_t& rh) {
     asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(rl), "=r"(rh) : "r"(al), "r"(ah), "r"(bl), "r"(bh));
 }
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack64(uint64_t v, uint32_t& lo, uint32_t& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 // Advance the linear engine one step and return the ++-scrambled 64-bit output as (hi, lo).
 template <int V>
-__device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, uint32_t& out_lo) {
+__device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, uint32_t& out_lo, uint32_t one = 1u) {
     // a = s0 + s3
     uint32_t al, ah;
-    add64(g.s0l, g.s0h, g.s3l, g.s3h, al, ah);
+    if (V & XO_ADD_WIDE) {
+        unpack64(mad_wide(g.s3l, one, pack64(g.s0l, g.s0h)), al, ah);
+        ah = mad_lo(g.s3h, one, ah);
+    } else {
+        add64(g.s0l, g.s0h, g.s3l, g.s3h, al, ah);
+    }
     // r = rotl(a, 23) + s0
-    const uint32_t rh = __funnelshift_l(al, ah, 23);
-    const uint32_t rl = __funnelshift_l(ah, al, 23);
-    add64(g.s0l, g.s0h, rl, rh, out_lo, out_hi);
+    if (V & XO_ROT_WIDE) {
+        // rotl(a,23) = (a.lo * 2^23 as 64 bits) + ((a.hi << 23) << 32) + (a.hi >> 9): three disjoint bit fields
+        uint32_t tl, th;
+        unpack64(mad_wide(al, 1u << 23, pack64(g.s0l, g.s0h)), tl, th);
+        th = mad_lo(ah, 1u << 23, th);
+        unpack64(mad_wide(ah >> 9, one, pack64(tl, th)), out_lo, out_hi);
+    } else {
+        const uint32_t rh = __funnelshift_l(al, ah, 23);
+        const uint32_t rl = __funnelshift_l(ah, al, 23);
+        add64(g.s0l, g.s0h, rl, rh, out_lo, out_hi);
+    }
     // t = s1 << 17
     uint32_t tl, th;
     if (V & XO_T_WIDE) {
-        asm("{\n\t.reg .b64 w;\n\tmul.wide.u32 w, %2, 131072;\n\tmov.b64 {%0, %1}, w;\n\t}" : "=r"(tl), "=r"(th) : "r"(g.s1l));
-        asm("mad.lo.u32 %0, %1, 131072, %0;" : "+r"(th) : "r"(g.s1h));
+        unpack64(mad_wide(g.s1l, 1u << 17, 0ull), tl, th);
+        th = mad_lo(g.s1h, 1u << 17, th);
     } else {
         tl = g.s1l << 17;
         th = __funnelshift_l(g.s1l, g.s1h, 17);
@@ -59,9 +101,16 @@ __device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, 
     g.s0l ^= x3l; g.s0h ^= x3h;
     g.s1l = n1l; g.s1h = n1h;
     g.s2l = n2l; g.s2h = n2h;
-    // rotl(x3, 45) = rotl(swap halves, 13)
-    g.s3h = __funnelshift_l(x3h, x3l, 13);
-    g.s3l = __funnelshift_l(x3l, x3h, 13);
+    // rotl(x3, 45) = rotl(y, 13) with y = x3 with its halves swapped (y.lo = x3h, y.hi = x3l)
+    if (V & XO_ROT45_WIDE) {
+        uint32_t rl, rh;
+        unpack64(mad_wide(x3h, 1u << 13, 0ull), rl, rh);            // (y.lo >> 19 : y.lo << 13)
+        g.s3h = mad_lo(x3l, 1u << 13, rh);                          // + y.hi << 13
+        g.s3l = mad_hi(x3l, 1u << 13, rl);                          // + y.hi >> 19 (disjoint from y.lo << 13)
+    } else {
+        g.s3h = __funnelshift_l(x3h, x3l, 13);
+        g.s3l = __funnelshift_l(x3l, x3h, 13);
+    }
 }
 
 constexpr int kXoVariant = 0;      // production choice (see profiles/ for the measurements behind it)
