@@ -37,7 +37,8 @@ typedef enum {
 #define MCB200_ANTITHETIC 1u    /* call_price_av / put_price_av estimator (mc_simd.rs:82-149) */
 
 /* ------------------------------------------------------------------ context ------------------------------------ */
-/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams.
+/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per resident thread:
+ * sm_count * ctas_per_sm * 256).
  * Thread slot i of the device uses substream jump^i(long_jump^substream_block(splitmix64(seed))): 2^128 draws per
  * thread, 2^64 thread slots per block, one block per GPU/rank (replaces per-chunk OS-entropy seeding,
  * mc_simd.rs:52-54).  Launches continue their substreams, so a fixed (seed, block, call sequence) is reproducible
@@ -49,7 +50,7 @@ const char *mcb200_last_error(void);
 
 typedef struct {
     int device, sm_count, ctas_per_sm, threads_per_cta;
-    int grid_slots;              /* resident CTAs the planner fills: sm_count * ctas_per_sm */
+    int grid_slots;              /* resident CTAs the planner fills: sm_count * ctas_per_sm (4 x 256 threads per SM) */
     int64_t pool_threads;        /* generator states held in HBM (32 bytes each) */
     uint64_t kernel_launches;    /* kernels launched by this context so far */
     uint64_t seed;
@@ -58,18 +59,22 @@ typedef struct {
 } mcb200_info;
 int mcb200_ctx_info(mcb200_ctx *ctx, mcb200_info *out);
 
-/* Launch plan for one batch: how (option, trial-slice) work items map onto the persistent grid.  Pure host logic. */
+/* Launch plan for one batch: how the work maps onto the resident warps.  Pure host logic.
+ * A "round" is 32 consecutive paths of one option (one per lane).  Round r belongs to option r / rounds_per_option;
+ * warp w (global warp index = CTA * 8 + warp in CTA) simulates rounds [w*R/W, (w+1)*R/W), R = total_rounds, W = warps,
+ * in order, drawing from the generator substream of global thread 32*w + lane. */
 typedef struct {
     int n_paths;                 /* 8 * floor(num_trials / 8) */
     int half_steps;              /* floor(steps) / 2 */
-    int slices;                  /* work items per option */
-    int paths_per_slice;
-    int paths_per_thread;        /* max over threads */
-    int grid;                    /* CTAs launched = min(grid_slots, n_options * slices) */
-    int64_t items;               /* n_options * slices */
+    int rounds_per_option;       /* ceil(n_paths / 32) */
+    int warps;                   /* W = min(8 * grid_slots, total_rounds): every warp owns at least one round */
+    int grid;                    /* CTAs launched = ceil(W / 8) */
+    int max_rounds_per_warp;     /* ceil(R / W): rounds differ by at most one between warps */
+    int64_t total_rounds;        /* R = n_options * rounds_per_option */
     double path_steps;           /* n_options * n_paths * 2 * half_steps: the throughput numerator */
 } mcb200_plan;
 int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan *out);
+int mcb200_plan_warp_range(const mcb200_plan *plan, int warp, int64_t *first_round, int64_t *end_round);
 
 /* ------------------------------------------------------------------ batched entry points (new) ----------------- */
 /* Host buffers: inputs are copied to the device, outputs copied back, the call returns when they are valid.
@@ -138,7 +143,7 @@ int mcb200_ctx_export_states(mcb200_ctx *ctx, int64_t first, int64_t count, uint
 
 /* Kernel timing for roofline accounting: when enabled, CUDA events are recorded on the launch stream immediately
  * before and after every simulate-kernel launch; mcb200_ctx_last_sim_ms() waits for the latest one and returns its
- * device duration in milliseconds (the fused path kernel alone, without the second-pass kernels). */
+ * device duration in milliseconds (the fused path + reduction + finalisation kernel, the only kernel of a batch). */
 int mcb200_ctx_set_timing(mcb200_ctx *ctx, int enabled);
 int mcb200_ctx_last_sim_ms(mcb200_ctx *ctx, float *ms_out);
 

@@ -32,8 +32,9 @@ class Info(C.Structure):
 
 
 class Plan(C.Structure):
-    _fields_ = [("n_paths", C.c_int), ("half_steps", C.c_int), ("slices", C.c_int), ("paths_per_slice", C.c_int),
-                ("paths_per_thread", C.c_int), ("grid", C.c_int), ("items", C.c_int64), ("path_steps", C.c_double)]
+    _fields_ = [("n_paths", C.c_int), ("half_steps", C.c_int), ("rounds_per_option", C.c_int), ("warps", C.c_int),
+                ("grid", C.c_int), ("max_rounds_per_warp", C.c_int), ("total_rounds", C.c_int64),
+                ("path_steps", C.c_double)]
 
 
 class Bumps(C.Structure):
@@ -77,6 +78,8 @@ def lib():
     L.mcb200_ctx_info.argtypes = [_vp, C.POINTER(Info)]
     L.mcb200_plan_query.restype = C.c_int
     L.mcb200_plan_query.argtypes = [C.c_int, _f, _f, C.c_int, C.POINTER(Plan)]
+    L.mcb200_plan_warp_range.restype = C.c_int
+    L.mcb200_plan_warp_range.argtypes = [C.POINTER(Plan), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mcb200_price_batch.restype = C.c_int
     L.mcb200_price_batch.argtypes = [_vp, C.c_int] + six + [_f, _f, C.c_uint] + [_fp] * 4
     L.mcb200_greeks_batch.restype = C.c_int

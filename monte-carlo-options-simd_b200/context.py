@@ -176,3 +176,13 @@ def plan_query(n_options, steps, num_trials, grid_slots):
     if st != 0:
         raise N.Mcb200Error(st, "invalid plan request")
     return {k: getattr(p, k) for k, _ in N.Plan._fields_}
+
+
+def plan_warp_range(plan, warp):
+    """Rounds [first, end) that global warp `warp` simulates under `plan` (a dict from plan_query)."""
+    p = N.Plan(**plan)
+    a, b = C.c_int64(), C.c_int64()
+    st = N.lib().mcb200_plan_warp_range(C.byref(p), int(warp), C.byref(a), C.byref(b))
+    if st != 0:
+        raise N.Mcb200Error(st, "invalid warp index")
+    return a.value, b.value

@@ -80,8 +80,9 @@ struct mcb200_ctx {
     uint64_t* pool = nullptr;     // grid_slots * kThreads states
     int64_t pool_threads = 0;
     uint64_t* d_jump = nullptr;   // jump polynomial table
-    double* partials = nullptr; size_t partials_cap = 0;      // doubles
-    double* moments = nullptr; size_t moments_cap = 0;        // doubles
+    double* slots = nullptr; size_t slots_cap = 0;            // doubles: per (warp, option) partial moment sums
+    unsigned* arrivals = nullptr; size_t arrivals_cap = 0;    // per-option arrival counters, zero between launches
+    double* moments = nullptr; size_t moments_cap = 0;        // doubles (only for the zero-path corner)
     float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned host / device)
     uint64_t launches = 0;
     bool timing = false; bool timed_once = false;
@@ -96,6 +97,18 @@ static int ensure(double** p, size_t* cap, size_t need) {
     size_t want = need + need / 2 + 1024;
     CU(cudaMalloc((void**)p, want * sizeof(double)));
     *cap = want;
+    return MCB200_OK;
+}
+
+static int ensure_arrivals(mcb200_ctx* c, size_t need) {
+    if (c->arrivals_cap >= need) return MCB200_OK;
+    if (c->arrivals) cudaFree(c->arrivals);
+    c->arrivals = nullptr; c->arrivals_cap = 0;
+    size_t want = need + need / 2 + 1024;
+    CU(cudaMalloc((void**)&c->arrivals, want * sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->arrivals, 0, want * sizeof(unsigned), c->stream));
+    CU(cudaStreamSynchronize(c->stream));        // launches may arrive on caller streams
+    c->arrivals_cap = want;
     return MCB200_OK;
 }
 
@@ -158,12 +171,13 @@ extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, ui
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "stream create failed"); break; }
         int occ_price = 0, occ_av = 0, occ_greeks = 0;
-        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_PRICE, false, 8>, &occ_price))) break;
-        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_AV, false, 8>, &occ_av))) break;
-        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_GREEKS, false, 8>, &occ_greeks))) break;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_PRICE, false>, &occ_price))) break;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_AV, false>, &occ_av))) break;
+        if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_GREEKS, false>, &occ_greeks))) break;
         int occ = occ_price < occ_av ? occ_price : occ_av;
         if (occ_greeks < occ) occ = occ_greeks;
         if (occ < 1) { rc = fail(MCB200_ERR_CUDA, "kernel occupancy query returned %d", occ); break; }
+        if (occ > kMinCtasPerSm) occ = kMinCtasPerSm;     // the design point (mcb200_pair.cuh); more residency buys nothing
         c->ctas_per_sm = occ;
         c->grid_slots = c->sm_count * occ;
         c->pool_threads = (int64_t)c->grid_slots * kThreads;
@@ -185,7 +199,8 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->pool) cudaFree(c->pool);
     if (c->d_jump) cudaFree(c->d_jump);
-    if (c->partials) cudaFree(c->partials);
+    if (c->slots) cudaFree(c->slots);
+    if (c->arrivals) cudaFree(c->arrivals);
     if (c->moments) cudaFree(c->moments);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
@@ -226,11 +241,36 @@ struct Request {
 
 template <int STREAM, int PAYOFF, bool DUMP>
 static void launch_sim(const SimArgs& a, int grid, cudaStream_t st) {
-    simulate_kernel<STREAM, PAYOFF, DUMP, 8><<<grid, kThreads, 0, st>>>(a);
+    simulate_kernel<STREAM, PAYOFF, DUMP><<<grid, kThreads, 0, st>>>(a);
 }
 
-// Simulate and reduce to per-option moment sums in `moments_out` (device, [n][2*n_est] doubles).
-static int run_moments(mcb200_ctx* c, const Request& rq, double* moments_out, cudaStream_t st, mcb200_plan* plan_out) {
+static FinalizeSpec make_finalize(int n_est, double n_paths, double num_trials, const float* rate, const float* years,
+                                  Bumps bumps, float* const* out, float* const* out_se) {
+    FinalizeSpec f{};
+    f.n_paths = n_paths; f.num_trials = num_trials; f.rate = rate; f.years = years; f.bumps = bumps;
+    for (int e = 0; e < EST_COUNT_GREEKS; ++e) {
+        f.out[e] = (e < n_est && out) ? out[e] : nullptr;
+        f.out_se[e] = (e < n_est && out_se) ? out_se[e] : nullptr;
+    }
+    return f;
+}
+
+static int run_finalize(mcb200_ctx* c, int n, int n_est, const double* moments, double n_paths, double num_trials,
+                        const float* rate, const float* years, Bumps bumps, float* const* out, float* const* out_se,
+                        cudaStream_t st) {
+    if (n == 0) return MCB200_OK;
+    const FinalizeSpec f = make_finalize(n_est, n_paths, num_trials, rate, years, bumps, out, out_se);
+    const int total = n * n_est;
+    finalize_kernel<<<(total + 127) / 128, 128, 0, st>>>(moments, n, n_est, f);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MCB200_OK;
+}
+
+// ONE launch per batch: simulate, reduce deterministically, then (finalize) write values and SEs and / or (moments_out)
+// the per-option moment sums [n][2*n_est].
+static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool finalize, float* const* out,
+                   float* const* out_se, cudaStream_t st, mcb200_plan* plan_out) {
     mcb200_plan pl;
     int rc = make_plan(rq.n, rq.steps, rq.num_trials, c->grid_slots, &pl);
     if (rc != MCB200_OK) return fail(rc, "invalid request: n=%d steps=%g num_trials=%g", rq.n, rq.steps, rq.num_trials);
@@ -239,14 +279,27 @@ static int run_moments(mcb200_ctx* c, const Request& rq, double* moments_out, cu
     const int n_acc = 2 * n_est;
     if (rq.n == 0) return MCB200_OK;
     if (pl.n_paths == 0) {
-        CU(cudaMemsetAsync(moments_out, 0, sizeof(double) * (size_t)rq.n * n_acc, st));
+        // nothing to simulate (num_trials < 8): all sums are zero, like the reference's empty map/reduce
+        double* mo = moments_out;
+        if (!mo) {
+            if ((rc = ensure(&c->moments, &c->moments_cap, (size_t)rq.n * n_acc))) return rc;
+            mo = c->moments;
+        }
+        CU(cudaMemsetAsync(mo, 0, sizeof(double) * (size_t)rq.n * n_acc, st));
+        if (finalize)
+            return run_finalize(c, rq.n, n_est, mo, 0.0, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out,
+                                out_se, st);
         return MCB200_OK;
     }
-    if ((rc = ensure(&c->partials, &c->partials_cap, (size_t)pl.items * n_acc))) return rc;
+    if ((rc = ensure(&c->slots, &c->slots_cap, ((size_t)pl.warps + (size_t)rq.n) * n_acc))) return rc;
+    if ((rc = ensure_arrivals(c, (size_t)rq.n))) return rc;
     SimArgs a{};
     a.opt = rq.opt; a.n_options = rq.n; a.n_paths = pl.n_paths; a.half_steps = pl.half_steps; a.steps = rq.steps;
-    a.slices = pl.slices; a.paths_per_slice = pl.paths_per_slice; a.bumps = rq.bumps; a.pool = c->pool;
-    a.chunk_seeds = rq.chunk_seeds; a.partials = c->partials; a.growth_out = rq.growth_out; a.one = 1u;
+    a.rounds_per_option = pl.rounds_per_option; a.total_rounds = pl.total_rounds; a.n_warps = pl.warps;
+    a.bumps = rq.bumps; a.pool = c->pool; a.chunk_seeds = rq.chunk_seeds; a.slots = c->slots; a.arrivals = c->arrivals;
+    a.moments_out = moments_out; a.finalize = finalize ? 1 : 0;
+    a.fin = make_finalize(n_est, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out, out_se);
+    a.growth_out = rq.growth_out;
     const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     switch (key) {
@@ -265,27 +318,6 @@ static int run_moments(mcb200_ctx* c, const Request& rq, double* moments_out, cu
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) { CU(cudaEventRecord(c->ev1, st)); c->timed_once = true; }
-    const int total = rq.n * n_acc;
-    sum_slices_kernel<<<(total + 255) / 256, 256, 0, st>>>(c->partials, rq.n, pl.slices, n_acc, moments_out);
-    c->launches++;
-    CU(cudaGetLastError());
-    return MCB200_OK;
-}
-
-static int run_finalize(mcb200_ctx* c, int n, int n_est, const double* moments, double n_paths, double num_trials,
-                        const float* rate, const float* years, Bumps bumps, float* const* out, float* const* out_se,
-                        cudaStream_t st) {
-    if (n == 0) return MCB200_OK;
-    FinalizeArgs f{};
-    f.moments = moments; f.n_options = n; f.n_est = n_est; f.n_paths = n_paths; f.num_trials = num_trials;
-    f.rate = rate; f.years = years; f.bumps = bumps;
-    for (int e = 0; e < EST_COUNT_GREEKS; ++e) {
-        f.out[e] = (e < n_est && out) ? out[e] : nullptr;
-        f.out_se[e] = (e < n_est && out_se) ? out_se[e] : nullptr;
-    }
-    finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(f);
-    c->launches++;
-    CU(cudaGetLastError());
     return MCB200_OK;
 }
 
@@ -304,13 +336,7 @@ static Bumps to_bumps(const mcb200_bumps* b) {
 
 // Device-resident core shared by every entry point.
 static int run_device(mcb200_ctx* c, const Request& rq, float* const* out, float* const* out_se, cudaStream_t st) {
-    const int n_est = rq.payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
-    int rc = ensure(&c->moments, &c->moments_cap, (size_t)(rq.n > 0 ? rq.n : 1) * 2 * n_est);
-    if (rc) return rc;
-    mcb200_plan pl;
-    if ((rc = run_moments(c, rq, c->moments, st, &pl))) return rc;
-    return run_finalize(c, rq.n, n_est, c->moments, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate,
-                        rq.opt.years, rq.bumps, out, out_se, st);
+    return run_sim(c, rq, nullptr, true, out, out_se, st, nullptr);
 }
 
 extern "C" int mcb200_price_batch_device(mcb200_ctx* c, int n, const float* spot, const float* strike,
@@ -361,7 +387,7 @@ extern "C" int mcb200_price_moments_device(mcb200_ctx* c, int n, const float* sp
     rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps;
     rq.num_trials = num_trials_local;
     rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
-    return run_moments(c, rq, moments, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
+    return run_sim(c, rq, moments, false, nullptr, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
 }
 
 extern "C" int mcb200_price_finalize_device(mcb200_ctx* c, int n, const float* rate, const float* years,

@@ -35,20 +35,33 @@ struct OptionArrays {          // struct-of-arrays option batch in HBM (f32, n e
 
 struct Bumps { float dspot, dvol, drate, dyears; };
 
+struct FinalizeSpec {       // how per-option moment sums become prices / Greeks (shared by the fused and the stand-alone pass)
+    double n_paths;          // paths simulated in total (all shards)
+    double num_trials;       // divisor, as passed by the caller (mc_simd.rs:77 divides by num_trials)
+    const float* rate; const float* years;
+    Bumps bumps;
+    float* out[EST_COUNT_GREEKS];      // estimator values (nullable)
+    float* out_se[EST_COUNT_GREEKS];   // their standard errors (nullable)
+};
+
 struct SimArgs {
     OptionArrays opt;
     int n_options;
-    int n_paths;           // 8 * floor(num_trials / 8): paths actually simulated per option (mc_simd.rs:49)
-    int half_steps;        // floor(steps) / 2 Box-Muller pairs per path (mc_simd.rs:47)
-    float steps;           // as passed (drift uses steps * nudt, mc_simd.rs:44)
-    int slices;            // CTAs' worth of work per option
-    int paths_per_slice;
+    int n_paths;             // 8 * floor(num_trials / 8): paths actually simulated per option (mc_simd.rs:49)
+    int half_steps;          // floor(steps) / 2 Box-Muller pairs per path (mc_simd.rs:47)
+    float steps;             // as passed (drift uses steps * nudt, mc_simd.rs:44)
+    int rounds_per_option;   // ceil(n_paths / 32): a round = 32 consecutive paths of one option = one pass of a warp
+    long long total_rounds;  // n_options * rounds_per_option
+    int n_warps;             // W <= min(gridDim.x * kWarps, R); warp w owns rounds [w*R/W, (w+1)*R/W)
     Bumps bumps;
-    uint64_t* pool;        // STREAM_FAST: per-thread generator states, 4 x u64 each, indexed by resident thread slot
+    uint64_t* pool;          // STREAM_FAST: per-thread generator states, 4 x u64 each, indexed by global thread id
     const uint64_t* chunk_seeds;   // STREAM_REF: n_options * n_paths/8 seeds of 32 x u64 (simd_rand layout)
-    double* partials;      // [n_options * slices][2 * kEst]
-    float* growth_out;     // DUMP only: [n_options][n_paths] terminal growth factors S_T / spot
-    uint32_t one;          // the value 1, delivered at run time so ptxas keeps IMAD.WIDE adds (mcb200_rng.cuh)
+    double* slots;           // [(n_warps + n_options)][2 * kEst]: partial sums of (warp w, option o) live in slot w + o
+    unsigned* arrivals;      // [n_options], zero on entry and on exit: segments of the option that have been flushed
+    double* moments_out;     // nullable: per-option moment sums [n_options][2 * kEst] (trials-sharded multi-GPU operation)
+    int finalize;            // non-zero: the last warp to finish an option also writes fin.out / fin.out_se
+    FinalizeSpec fin;
+    float* growth_out;       // DUMP only: [n_options][n_paths] terminal growth factors S_T / spot
 };
 
 // f32 constants exactly as the reference computes them (mc_simd.rs:36-45), then rescaled to base-2 exponent units.
@@ -65,14 +78,14 @@ __device__ __forceinline__ LegConst leg_constants(float vol, float rate, float d
     return c;
 }
 
-// ------------------------------------------------------------------------------------------------ constants in smem
+// ------------------------------------------------------------------------------------------------ per-option constants
 // PRICE / AV : [0]=spot [1]=strike [2]=c2 [3]=d2
 // GREEKS     : [0]=spot [1]=strike [2]=c2 [3]=d2 [4]=dspot
 //              [5..8]  = c2,d2 for vol+h ; c2,d2 for vol-h
 //              [9,10]  = d2 for r+h, r-h          [11,12] = exp(-(r+h)T), exp(-(r-h)T)
 //              [13..16]= c2,d2 for T+h ; c2,d2 for T-h    [17,18] = exp(-r(T+h)), exp(-r(T-h))
 template <int STREAM, int PAYOFF>
-__device__ __forceinline__ void load_item_constants(const SimArgs& a, int o, float* sc) {
+__device__ __forceinline__ void load_option_constants(const SimArgs& a, int o, float* sc) {
     const float spot = a.opt.spot[o], strike = a.opt.strike[o], vol = a.opt.vol[o];
     const float rate = a.opt.rate[o], years = a.opt.years[o], div = a.opt.div[o];
     const LegConst base = leg_constants<STREAM>(vol, rate, div, years / a.steps, a.steps);
@@ -96,176 +109,222 @@ __device__ __forceinline__ void load_item_constants(const SimArgs& a, int o, flo
     }
 }
 
-__device__ __forceinline__ void accumulate(float* acc, int est, float x) {
-    // acc is this thread's column of the [2*kEst][kThreads] shared accumulator tile
-    acc[(2 * est) * kThreads] += x;
-    acc[(2 * est + 1) * kThreads] = fmaf(x, x, acc[(2 * est + 1) * kThreads]);
-}
+// acc[2e] += x ; acc[2e+1] += x*x  -- per-thread fp32 moment registers of estimator e
+#define MCB_ACC(e, x) do { const float x_ = (x); acc[2 * (e)] += x_; acc[2 * (e) + 1] = fmaf(x_, x_, acc[2 * (e) + 1]); } while (0)
 
 // Payoff evaluation for one finished path; m = accumulated Box-Muller sum.  Returns the base growth factor.
+// sc points at registers (PRICE / AV) or at the warp's shared-memory constants (GREEKS).
 template <int PAYOFF>
-__device__ __forceinline__ float evaluate_path(float m, const float* sc, float* acc) {
+__device__ __forceinline__ float evaluate_path(float m, const float* sc, float (&acc)[2 * PayoffTraits<PAYOFF>::kEst]) {
     const float spot = sc[0], strike = sc[1];
     const float g0 = mufu_ex2(fmaf(m, sc[2], sc[3]));
     const float a0 = fmaf(spot, g0, -strike);                // S_T - K
     if (PAYOFF == PAYOFF_PRICE) {
-        accumulate(acc, EST_CALL, fmaxf(a0, 0.0f));          // max(S_T - K, 0)            (mc_simd.rs:62-69)
-        accumulate(acc, EST_PUT, fmaxf(-a0, 0.0f));          // max(-S_T + K, 0): call_mult = -1
+        MCB_ACC(EST_CALL, fmaxf(a0, 0.0f));                  // max(S_T - K, 0)            (mc_simd.rs:62-69)
+        MCB_ACC(EST_PUT, fmaxf(-a0, 0.0f));                  // max(-S_T + K, 0): call_mult = -1
     } else if (PAYOFF == PAYOFF_AV) {
         const float g1 = mufu_ex2(fmaf(-m, sc[2], sc[3]));   // antithetic leg: -sqrt(2)*sidt (mc_simd.rs:103)
         const float a1 = fmaf(spot, g1, -strike);
-        accumulate(acc, EST_CALL, 0.5f * (fmaxf(a0, 0.0f) + fmaxf(a1, 0.0f)));
-        accumulate(acc, EST_PUT, 0.5f * (fmaxf(-a0, 0.0f) + fmaxf(-a1, 0.0f)));
+        MCB_ACC(EST_CALL, 0.5f * (fmaxf(a0, 0.0f) + fmaxf(a1, 0.0f)));
+        MCB_ACC(EST_PUT, 0.5f * (fmaxf(-a0, 0.0f) + fmaxf(-a1, 0.0f)));
     } else {
-        accumulate(acc, EST_CALL, fmaxf(a0, 0.0f));
-        accumulate(acc, EST_PUT, fmaxf(-a0, 0.0f));
+        MCB_ACC(EST_CALL, fmaxf(a0, 0.0f));
+        MCB_ACC(EST_PUT, fmaxf(-a0, 0.0f));
         // spot +-h share g0 (mc_simd.rs:196-213).  With b = h*g0: pay(S+h) - pay(S-h) = min(max(a0+b,0), 2b) and
         // pay(S+h) - 2 pay(S) + pay(S-h) = max(b - |a0|, 0): the same central differences, without cancellation.
         const float b = sc[4] * g0;
         const float dcall = fminf(fmaxf(a0 + b, 0.0f), 2.0f * b);
-        accumulate(acc, EST_CALL_DELTA, dcall);
-        accumulate(acc, EST_PUT_DELTA, dcall - 2.0f * b);    // put(S+h) - put(S-h) = call diff - 2 h g0
-        accumulate(acc, EST_GAMMA, fmaxf(b - fabsf(a0), 0.0f));
+        MCB_ACC(EST_CALL_DELTA, dcall);
+        MCB_ACC(EST_PUT_DELTA, dcall - 2.0f * b);            // put(S+h) - put(S-h) = call diff - 2 h g0
+        MCB_ACC(EST_GAMMA, fmaxf(b - fabsf(a0), 0.0f));
         // vol +-h: both drift and diffusion change (mc_simd.rs:242-250), call only
         const float gvp = mufu_ex2(fmaf(m, sc[5], sc[6])), gvm = mufu_ex2(fmaf(m, sc[7], sc[8]));
-        accumulate(acc, EST_VEGA, fmaxf(fmaf(spot, gvp, -strike), 0.0f) - fmaxf(fmaf(spot, gvm, -strike), 0.0f));
+        MCB_ACC(EST_VEGA, fmaxf(fmaf(spot, gvp, -strike), 0.0f) - fmaxf(fmaf(spot, gvm, -strike), 0.0f));
         // r +-h: drift changes, each leg discounted with its own rate (mc_simd.rs:328-329,384-385)
         const float arp = fmaf(spot, mufu_ex2(fmaf(m, sc[2], sc[9])), -strike);
         const float arm = fmaf(spot, mufu_ex2(fmaf(m, sc[2], sc[10])), -strike);
-        accumulate(acc, EST_CALL_RHO, sc[11] * fmaxf(arp, 0.0f) - sc[12] * fmaxf(arm, 0.0f));
-        accumulate(acc, EST_PUT_RHO, sc[11] * fmaxf(-arp, 0.0f) - sc[12] * fmaxf(-arm, 0.0f));
+        MCB_ACC(EST_CALL_RHO, sc[11] * fmaxf(arp, 0.0f) - sc[12] * fmaxf(arm, 0.0f));
+        MCB_ACC(EST_PUT_RHO, sc[11] * fmaxf(-arp, 0.0f) - sc[12] * fmaxf(-arm, 0.0f));
         // T +-h: dt, drift, diffusion and discount change (mc_simd.rs:402-413,470-471); theta = (P(T-h) - P(T+h)) / 2h
         const float atp = fmaf(spot, mufu_ex2(fmaf(m, sc[13], sc[14])), -strike);
         const float atm = fmaf(spot, mufu_ex2(fmaf(m, sc[15], sc[16])), -strike);
-        accumulate(acc, EST_CALL_THETA, sc[18] * fmaxf(atm, 0.0f) - sc[17] * fmaxf(atp, 0.0f));
-        accumulate(acc, EST_PUT_THETA, sc[18] * fmaxf(-atm, 0.0f) - sc[17] * fmaxf(-atp, 0.0f));
+        MCB_ACC(EST_CALL_THETA, sc[18] * fmaxf(atm, 0.0f) - sc[17] * fmaxf(atp, 0.0f));
+        MCB_ACC(EST_PUT_THETA, sc[18] * fmaxf(-atm, 0.0f) - sc[17] * fmaxf(-atp, 0.0f));
     }
     return g0;
 }
 
+// ------------------------------------------------------------------------------------------------ finalisation
+// mean = sum / num_trials * scale ; se = sample std of the per-path estimator / sqrt(n) * (n / num_trials) * scale
+__device__ __forceinline__ void finalize_estimator(const FinalizeSpec& f, int o, int e, double s, double ss) {
+    const float disc = expf(-f.rate[o] * f.years[o]);             // mc_simd.rs:77
+    double scale;
+    switch (e) {
+        case EST_CALL: case EST_PUT: scale = disc; break;
+        case EST_CALL_DELTA: case EST_PUT_DELTA: scale = (double)disc / (2.0 * f.bumps.dspot); break;      // :592,618
+        case EST_GAMMA: scale = (double)disc / ((double)f.bumps.dspot * f.bumps.dspot); break;              // :644
+        case EST_VEGA: scale = (double)disc / (200.0 * f.bumps.dvol); break;                                // :670
+        case EST_CALL_RHO: case EST_PUT_RHO: scale = 1.0 / (200.0 * f.bumps.drate); break;                  // :698,725
+        default: scale = 1.0 / (2.0 * f.bumps.dyears); break;                                               // :752,778
+    }
+    const double n = f.n_paths;
+    const double mu = n > 0.0 ? s / n : 0.0;
+    double var = n > 1.0 ? (ss - n * mu * mu) / (n - 1.0) : 0.0;
+    var = var > 0.0 ? var : 0.0;
+    if (f.out[e]) f.out[e][o] = (float)(s / f.num_trials * scale);
+    if (f.out_se[e]) f.out_se[e][o] = n > 0.0 ? (float)(sqrt(var / n) * (n / f.num_trials) * fabs(scale)) : 0.0f;
+}
+
+// Stand-alone pass over moment sums that are already complete (after a cross-GPU all-reduce, or when no path was run).
+__global__ void finalize_kernel(const double* __restrict__ moments, int n_options, int n_est, const FinalizeSpec f) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_options * n_est) return;
+    const int o = idx / n_est, e = idx - o * n_est;
+    finalize_estimator(f, o, e, moments[(size_t)idx * 2], moments[(size_t)idx * 2 + 1]);
+}
+
+// Rounds [w*R/W, (w+1)*R/W) belong to warp w; the warp that owns round r is therefore ceil((r+1)*W/R) - 1.
+__device__ __forceinline__ long long round_begin(long long w, long long R, long long W) { return w * R / W; }
+__device__ __forceinline__ int owner_warp(long long r, long long R, long long W) { return (int)(((r + 1) * W - 1) / R); }
+
 // ------------------------------------------------------------------------------------------------ the fused kernel
-// Persistent CTAs: CTA c works on items c, c + gridDim.x, ... where item = (option, slice).  Thread t of the CTA
-// simulates paths slice_base + t + 256*j.  In STREAM_FAST every thread owns one generator stream for the whole
-// launch (state loaded from / stored back to the pool, so consecutive launches continue the same substreams).
-template <int STREAM, int PAYOFF, bool DUMP, int MIN_CTAS>
-__global__ void __launch_bounds__(kThreads, MIN_CTAS) simulate_kernel(const SimArgs a) {
+// One launch does the whole batch: simulate, reduce, finalise.
+//   * work unit = a "round": 32 consecutive paths of one option, one path per lane.  The n_options * ceil(n_paths/32)
+//     rounds are dealt to the resident warps in contiguous, equal (+-1) ranges, so every SM sub-partition gets the same
+//     load whatever the batch shape (no CTA-level quantisation, no block barrier anywhere in the path loop);
+//   * every thread owns one generator stream for the whole launch (state loaded from / stored back to the pool, so
+//     consecutive launches continue the same substreams) and keeps its fp32 moment sums in registers;
+//   * when a warp leaves an option it reduces its sums (fp64, butterfly) into slot (warp + option) and bumps the
+//     option's arrival counter; the warp that completes the count sums the option's slots in warp order (fixed order:
+//     bit-reproducible, independent of which warp arrives last) and writes moments and/or final values and SEs.
+// Path data never leaves registers.
+template <int STREAM, int PAYOFF, bool DUMP>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const SimArgs a) {
     constexpr int kEst = PayoffTraits<PAYOFF>::kEst;
     constexpr int kAcc = 2 * kEst;
-    __shared__ float s_acc[kAcc * kThreads];
-    __shared__ float s_const[PayoffTraits<PAYOFF>::kConst];
-    __shared__ double s_warp[kWarps][kAcc];
+    constexpr int kConst = PayoffTraits<PAYOFF>::kConst;
+    constexpr bool kConstInSmem = PAYOFF == PAYOFF_GREEKS;
+    __shared__ float s_const[kConstInSmem ? kWarps * kConst : 1];
 
-    const int t = threadIdx.x;
-    const uint32_t one = a.one;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long R = a.total_rounds, W = a.n_warps;
+    if (w >= a.n_warps) return;                              // tail of the last CTA when W is not a multiple of 8
+    long long r = round_begin(w, R, W);
+    const long long r_end = round_begin(w + 1, R, W);        // W <= R: never empty
+
     Xoshiro256 g;
-    if (STREAM == STREAM_FAST) xoshiro_load(g, a.pool + 4ull * ((size_t)blockIdx.x * kThreads + t));
+    const size_t gtid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (STREAM == STREAM_FAST) xoshiro_load(g, a.pool + 4ull * gtid);
 
-    const int n_items = a.n_options * a.slices;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int o = item / a.slices, slice = item - o * a.slices;
-        __syncthreads();                                   // previous item's s_const / s_warp readers are done
-        if (t == 0) load_item_constants<STREAM, PAYOFF>(a, o, s_const);
-#pragma unroll
-        for (int k = 0; k < kAcc; ++k) s_acc[k * kThreads + t] = 0.0f;
-        __syncthreads();
+    float creg[kConstInSmem ? 1 : kConst];
+    float* sc = kConstInSmem ? s_const + (threadIdx.x >> 5) * kConst : creg;
+    float acc[kAcc];
+    int o = (int)(r / a.rounds_per_option);
+    int k = (int)(r - (long long)o * a.rounds_per_option);   // round index inside option o
+    bool enter = true;                                       // constants of option o not loaded yet
+    bool fresh = true;                                       // next flush is the first of this (warp, option) segment
 
-        const int p_begin = slice * a.paths_per_slice;
-        const int p_end = min(p_begin + a.paths_per_slice, a.n_paths);
-        for (int p = p_begin + t; p < p_end; p += kThreads) {
-            if (STREAM == STREAM_REF) {
-                // simd_rand seed layout: word k of lane l at u64 index 8*k + l of the chunk's 32-word seed
-                const uint64_t* seed = a.chunk_seeds + ((size_t)o * (a.n_paths >> 3) + (p >> 3)) * 32 + (p & 7);
-                const uint64_t w0 = seed[0], w1 = seed[8], w2 = seed[16], w3 = seed[24];
-                g.s0l = (uint32_t)w0; g.s0h = (uint32_t)(w0 >> 32); g.s1l = (uint32_t)w1; g.s1h = (uint32_t)(w1 >> 32);
-                g.s2l = (uint32_t)w2; g.s2h = (uint32_t)(w2 >> 32); g.s3l = (uint32_t)w3; g.s3h = (uint32_t)(w3 >> 32);
-            }
-            float m = 0.0f;
-            if (STREAM == STREAM_FAST) {
-#pragma unroll 4
-                for (int i = 0; i < a.half_steps; ++i) m = pair_fast(g, m, one);
+    while (r < r_end) {
+        if (enter) {
+            if (kConstInSmem) {
+                __syncwarp();
+                if (lane == 0) load_option_constants<STREAM, PAYOFF>(a, o, sc);
+                __syncwarp();
             } else {
+                load_option_constants<STREAM, PAYOFF>(a, o, sc);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kAcc; ++i) acc[i] = 0.0f;
+
+        // ---- a run of this warp's rounds inside option o (bounded so that the fp32 sums stay well conditioned)
+        long long left = r_end - r;
+        int n_run = a.rounds_per_option - k;
+        if ((long long)n_run > left) n_run = (int)left;
+        if (n_run > kMaxRoundsPerFlush) n_run = kMaxRoundsPerFlush;
+        for (int j = 0; j < n_run; ++j, ++k) {
+            const int p = k * 32 + lane;
+            if (p < a.n_paths) {
+                if (STREAM == STREAM_REF) {
+                    // simd_rand seed layout: word j of lane l at u64 index 8*j + l of the chunk's 32-word seed
+                    const uint64_t* seed = a.chunk_seeds + ((size_t)o * (a.n_paths >> 3) + (p >> 3)) * 32 + (p & 7);
+                    const uint64_t w0 = seed[0], w1 = seed[8], w2 = seed[16], w3 = seed[24];
+                    g.s0l = (uint32_t)w0; g.s0h = (uint32_t)(w0 >> 32); g.s1l = (uint32_t)w1; g.s1h = (uint32_t)(w1 >> 32);
+                    g.s2l = (uint32_t)w2; g.s2h = (uint32_t)(w2 >> 32); g.s3l = (uint32_t)w3; g.s3h = (uint32_t)(w3 >> 32);
+                }
+                float m = 0.0f;
+                if (STREAM == STREAM_FAST) {
+#pragma unroll 8
+                    for (int i = 0; i < a.half_steps; ++i) m = pair_fast(g, m);
+                } else {
 #pragma unroll 2
-                for (int i = 0; i < a.half_steps; ++i) m = pair_ref(g, m);
+                    for (int i = 0; i < a.half_steps; ++i) m = pair_ref(g, m);
+                }
+                const float g0 = evaluate_path<PAYOFF>(m, sc, acc);
+                if (DUMP) a.growth_out[(size_t)o * a.n_paths + p] = g0;
             }
-            const float g0 = evaluate_path<PAYOFF>(m, s_const, s_acc + t);
-            if (DUMP) a.growth_out[(size_t)o * a.n_paths + p] = g0;
         }
+        r += n_run;
+        const bool option_done = (k == a.rounds_per_option);
+        const bool segment_done = option_done || r == r_end;
 
-        // deterministic reduction: fp32 thread sums -> fp64, butterfly within the warp (4 accumulators at a time to
-        // bound register use), then a fixed-order sum across the 8 warps
-#pragma unroll 1
-        for (int k0 = 0; k0 < kAcc; k0 += 4) {
-            double v[4];
+        // ---- flush: fp32 thread sums -> fp64, butterfly within the warp; lane i keeps accumulator i
+        double mine = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (double)s_acc[(k0 + k) * kThreads + t];
+        for (int i = 0; i < kAcc; ++i) {
+            double v = (double)acc[i];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == i) mine = v;
+        }
+        double* slot = a.slots + ((size_t)w + (size_t)o) * kAcc;
+        if (lane < kAcc) {
+            if (!fresh) mine += slot[lane];                  // only this warp touches the slot before its arrival
+            slot[lane] = mine;
+        }
+        if (segment_done) {
+            // publish the slot and count the arrival; the warp that completes the option finishes it
+            __threadfence();
+            __syncwarp();
+            const long long first_round = (long long)o * a.rounds_per_option;
+            const int w_first = owner_warp(first_round, R, W);
+            const int w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(a.arrivals + o, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if ((int)prev == w_last - w_first) {
+                __threadfence();
+                double s = 0.0;
+                if (w_last - w_first < 64) {
+                    if (lane < kAcc)
+                        for (int ww = w_first; ww <= w_last; ++ww)
+                            s += __ldcg(a.slots + ((size_t)ww + (size_t)o) * kAcc + lane);
+                } else {
+                    // many segments (few options, huge trial counts): lanes stride over the warps, fixed butterfly
+                    for (int i = 0; i < kAcc; ++i) {
+                        double t = 0.0;
+                        for (int ww = w_first + lane; ww <= w_last; ww += 32)
+                            t += __ldcg(a.slots + ((size_t)ww + (size_t)o) * kAcc + i);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
-            }
-            if ((t & 31) == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s_warp[t >> 5][k0 + k] = v[k];
+                        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        t = __shfl_sync(0xffffffffu, t, 0);
+                        if (lane == i) s = t;
+                    }
+                }
+                if (a.moments_out && lane < kAcc) a.moments_out[(size_t)o * kAcc + lane] = s;
+                if (a.finalize) {
+                    const double sum = __shfl_sync(0xffffffffu, s, (2 * lane) & 31);
+                    const double sq = __shfl_sync(0xffffffffu, s, (2 * lane + 1) & 31);
+                    if (lane < kEst) finalize_estimator(a.fin, o, lane, sum, sq);
+                }
+                if (lane == 0) a.arrivals[o] = 0u;           // leave the counter clean for the next launch
             }
         }
-        __syncthreads();
-        if (t < kAcc) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += s_warp[w][t];
-            a.partials[(size_t)item * kAcc + t] = s;
-        }
+        if (option_done) { ++o; k = 0; enter = true; fresh = true; }
+        else { enter = false; fresh = false; }
     }
-    if (STREAM == STREAM_FAST) xoshiro_store(g, a.pool + 4ull * ((size_t)blockIdx.x * kThreads + t));
-}
-
-// ------------------------------------------------------------------------------------------------ second pass
-// Fixed-order sum over an option's slices (index order, fp64) -> per-option moment sums [n_options][2*kEst].
-__global__ void sum_slices_kernel(const double* __restrict__ partials, int n_options, int slices, int n_acc,
-                                  double* __restrict__ moments) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_options * n_acc) return;
-    const int o = idx / n_acc, k = idx - o * n_acc;
-    double s = 0.0;
-    for (int sl = 0; sl < slices; ++sl) s += partials[((size_t)o * slices + sl) * n_acc + k];
-    moments[idx] = s;
-}
-
-struct FinalizeArgs {
-    const double* moments;   // [n_options][2*n_est], possibly summed over several devices
-    int n_options;
-    int n_est;
-    double n_paths;          // paths simulated in total (all shards)
-    double num_trials;       // divisor, as passed by the caller (mc_simd.rs:77 divides by num_trials)
-    const float* rate; const float* years;
-    Bumps bumps;
-    float* out[EST_COUNT_GREEKS];      // estimator values (nullable)
-    float* out_se[EST_COUNT_GREEKS];   // their standard errors (nullable)
-};
-
-// mean = sum / num_trials * scale ; se = sample std of the per-path estimator / sqrt(n) * (n / num_trials) * scale
-__global__ void finalize_kernel(const FinalizeArgs f) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= f.n_options) return;
-    const float disc = expf(-f.rate[o] * f.years[o]);             // mc_simd.rs:77
-    const double n = f.n_paths;
-    for (int e = 0; e < f.n_est; ++e) {
-        double scale;
-        switch (e) {
-            case EST_CALL: case EST_PUT: scale = disc; break;
-            case EST_CALL_DELTA: case EST_PUT_DELTA: scale = (double)disc / (2.0 * f.bumps.dspot); break;      // :592,618
-            case EST_GAMMA: scale = (double)disc / ((double)f.bumps.dspot * f.bumps.dspot); break;              // :644
-            case EST_VEGA: scale = (double)disc / (200.0 * f.bumps.dvol); break;                                // :670
-            case EST_CALL_RHO: case EST_PUT_RHO: scale = 1.0 / (200.0 * f.bumps.drate); break;                  // :698,725
-            default: scale = 1.0 / (2.0 * f.bumps.dyears); break;                                               // :752,778
-        }
-        const double s = f.moments[((size_t)o * f.n_est + e) * 2], ss = f.moments[((size_t)o * f.n_est + e) * 2 + 1];
-        const double mu = n > 0.0 ? s / n : 0.0;
-        double var = n > 1.0 ? (ss - n * mu * mu) / (n - 1.0) : 0.0;
-        var = var > 0.0 ? var : 0.0;
-        if (f.out[e]) f.out[e][o] = (float)(s / f.num_trials * scale);
-        if (f.out_se[e]) f.out_se[e][o] = n > 0.0 ? (float)(sqrt(var / n) * (n / f.num_trials) * fabs(scale)) : 0.0f;
-    }
+    if (STREAM == STREAM_FAST) xoshiro_store(g, a.pool + 4ull * gtid);
 }
 
 // ------------------------------------------------------------------------------------------------ RNG substreams

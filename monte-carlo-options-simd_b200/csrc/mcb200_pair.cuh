@@ -10,6 +10,11 @@ namespace mcb200 {
 
 constexpr int kThreads = 256;          // threads per CTA (8 warps, 2 per SM sub-partition)
 constexpr int kWarps = kThreads / 32;
+// Resident CTAs per SM the path kernels are compiled for: 4 x 256 threads = 64 registers per thread.  The inner step
+// is bound by the ALU pipe, not by latency: measured 3.32 pairs/clk/SM at 8 CTAs/SM and 3.32 at 4 with unroll 8
+// (profiles/r1_microbench_v2_pipes.json), so half occupancy costs nothing and buys register-resident accumulators.
+constexpr int kMinCtasPerSm = 4;
+constexpr int kMaxRoundsPerFlush = 4096;   // paths a thread sums in fp32 before its moments go to fp64
 
 // ------------------------------------------------------------------------------------------------ math helpers
 __device__ __forceinline__ float mufu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -75,8 +80,8 @@ __device__ __forceinline__ float pair_fast_v(Xoshiro256& g, float acc, uint32_t 
 
 constexpr int kFloatMode = 0;  // production choice
 
-__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc, uint32_t one) {
-    return pair_fast_v<kXoVariant, kFloatMode>(g, acc, one << 23, one);
+__device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc) {
+    return pair_fast_v<kXoVariant, kFloatMode>(g, acc);
 }
 
 // Reference-stream pair update: consumes the generator exactly like rand32x8.rs:5-21 + mc_simd.rs:9-21

@@ -1,11 +1,11 @@
-// mcb200_plan.cpp -- launch planner: maps (options x trials) onto the persistent grid.  Pure host logic, no CUDA.
+// mcb200_plan.cpp -- launch planner: maps (options x trials) onto the resident warps.  Pure host logic, no CUDA.
 //
 // The reference fans 8-path chunks of ONE option out over a thread pool (rayon, /root/reference/src/mc_simd.rs:49-51)
-// and prices options one call at a time (benches/benchmark.rs:40-42).  Here a whole batch is one launch: each option
-// is cut into `slices` equal trial ranges, each (option, slice) item is simulated by one 256-thread CTA, and the
-// persistent grid walks the items round-robin.  The slice count is chosen to minimise the makespan
-//     waves(items / grid_slots) * paths_per_thread
-// so that both many-option batches (slices = 1) and few-option / huge-trial requests fill all 148 SMs.
+// and prices options one call at a time (benches/benchmark.rs:40-42).  Here a whole batch is one launch.  The unit of
+// work is a "round": 32 consecutive paths of one option (one per lane of a warp).  The n_options * ceil(n_paths/32)
+// rounds are dealt to the W resident warps in contiguous ranges  [w*R/W, (w+1)*R/W)  -- equal to within one round --
+// so the load of every SM sub-partition is the same whatever the shape of the batch: 1e5 options x 1e4 trials and
+// 1 option x 1e8 trials both fill all 148 SMs.  The kernel (mcb200_kernels.cuh) evaluates the same formulas.
 #include <cmath>
 #include <cstdint>
 #include "../../include/mcb200.h"
@@ -27,36 +27,36 @@ int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb2
     p.half_steps = half_steps;
     p.path_steps = (double)n_options * (double)n_paths * 2.0 * (double)half_steps;
     if (n_options == 0 || n_paths == 0) {
-        p.slices = 1; p.paths_per_slice = 0; p.paths_per_thread = 0; p.grid = 0; p.items = n_options;
-        *out = p;
+        *out = p;                                                        // nothing to launch
         return MCB200_OK;
     }
-    const long long T = kPlanThreads;
-    const long long s_min = ceil_div(n_paths, T * kPlanMaxPathsPerThread);
-    long long s_max = ceil_div(n_paths, T);                              // one path per thread
-    if (s_max > s_min + 4ll * grid_slots) s_max = s_min + 4ll * grid_slots;
-    // per-item fixed cost (constants, reduction) expressed in issue slots, per-pair cost ~28 slots
-    const long long pair_cost = 28, path_cost = 48, item_cost = 900;
-    long long best_s = s_min, best_cost = -1;
-    for (long long s = s_min; s <= s_max; ++s) {
-        const long long pps = ceil_div(n_paths, s);
-        const long long ppt = ceil_div(pps, T);
-        const long long waves = ceil_div((long long)n_options * s, grid_slots);
-        const long long cost = waves * (ppt * (half_steps * pair_cost + path_cost) + item_cost);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
-    }
-    p.slices = (int)best_s;
-    p.paths_per_slice = (int)ceil_div(n_paths, best_s);
-    p.paths_per_thread = (int)ceil_div(p.paths_per_slice, T);
-    p.items = (long long)n_options * best_s;
-    if (p.items > 0x7fffffffll) return MCB200_ERR_INVALID;
-    p.grid = (int)(p.items < grid_slots ? p.items : grid_slots);
+    p.rounds_per_option = (int)ceil_div(n_paths, 32);
+    p.total_rounds = (long long)n_options * p.rounds_per_option;
+    // W <= R, so that every warp owns at least one round (the arrival counts of the kernel rely on it)
+    const long long resident = (long long)grid_slots * kPlanWarps;
+    p.warps = (int)(p.total_rounds < resident ? p.total_rounds : resident);
+    p.grid = (int)ceil_div(p.warps, kPlanWarps);
+    p.max_rounds_per_warp = (int)ceil_div(p.total_rounds, p.warps);
+    if (p.total_rounds > (1ll << 62) / p.warps) return MCB200_ERR_INVALID;   // (r+1)*W must fit in 64 bits
     *out = p;
     return MCB200_OK;
+}
+
+void plan_warp_range(const mcb200_plan* p, int warp, long long* first, long long* last) {
+    *first = (long long)warp * p->total_rounds / p->warps;
+    *last = ((long long)warp + 1) * p->total_rounds / p->warps;
 }
 
 }  // namespace mcb200
 
 extern "C" int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan* out) {
     return mcb200::make_plan(n_options, steps, num_trials, grid_slots, out);
+}
+
+extern "C" int mcb200_plan_warp_range(const mcb200_plan* plan, int warp, int64_t* first_round, int64_t* end_round) {
+    if (!plan || !first_round || !end_round || plan->warps <= 0 || warp < 0 || warp >= plan->warps) return MCB200_ERR_INVALID;
+    long long a, b;
+    mcb200::plan_warp_range(plan, warp, &a, &b);
+    *first_round = a; *end_round = b;
+    return MCB200_OK;
 }

@@ -3,7 +3,7 @@
 #include "../../include/mcb200.h"
 
 namespace mcb200 {
-constexpr int kPlanThreads = 256;              // must equal kThreads in mcb200_kernels.cuh
-constexpr int kPlanMaxPathsPerThread = 4096;   // keeps the per-thread fp32 payoff sums well conditioned
+constexpr int kPlanWarps = 8;                  // warps per CTA; must equal kWarps in mcb200_pair.cuh
 int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan* out);
+void plan_warp_range(const mcb200_plan* p, int warp, long long* first, long long* last);
 }

@@ -53,10 +53,11 @@ def test_python_mirror_has_reference_api(pkg):
 
 
 def test_planner_reference_chunking(pkg):
-    """paths = 8*floor(trials/8), pairs = floor(steps)/2 (mc_simd.rs:47,49); every path is covered exactly once."""
-    for n, steps, trials, slots in [(112, 100.0, 1000.0, 1184), (112, 100.0, 20000.0, 1184), (112, 1000.0, 2000.0, 1184),
-                                    (4096, 252.0, 1e5, 1184), (100000, 252.0, 1e6, 1184), (1, 101.0, 1007.0, 1184),
-                                    (3, 7.0, 8.0, 16), (1, 252.0, 1e6, 1184), (5, 100.0, 3.0, 1184)]:
+    """paths = 8*floor(trials/8), pairs = floor(steps)/2 (mc_simd.rs:47,49); the warp ranges tile the rounds exactly
+    once, in order, and differ in length by at most one round."""
+    for n, steps, trials, slots in [(112, 100.0, 1000.0, 592), (112, 100.0, 20000.0, 592), (112, 1000.0, 2000.0, 592),
+                                    (4096, 252.0, 1e5, 592), (100000, 252.0, 1e6, 592), (1, 101.0, 1007.0, 592),
+                                    (3, 7.0, 8.0, 16), (1, 252.0, 1e6, 592), (5, 100.0, 3.0, 592), (7, 10.0, 40.0, 2)]:
         p = pkg.plan_query(n, steps, trials, slots)
         assert p["n_paths"] == 8 * (int(trials) // 8)
         assert p["half_steps"] == int(steps) // 2
@@ -64,23 +65,40 @@ def test_planner_reference_chunking(pkg):
         if p["n_paths"] == 0:
             assert p["grid"] == 0
             continue
-        assert p["slices"] * p["paths_per_slice"] >= p["n_paths"]
-        assert (p["slices"] - 1) * p["paths_per_slice"] < p["n_paths"]
-        assert p["paths_per_thread"] == math.ceil(p["paths_per_slice"] / 256) <= 4096
-        assert p["items"] == n * p["slices"] and p["grid"] == min(slots, p["items"])
+        assert p["rounds_per_option"] == math.ceil(p["n_paths"] / 32)
+        assert p["total_rounds"] == n * p["rounds_per_option"]
+        assert p["warps"] == min(8 * slots, p["total_rounds"]) and p["grid"] == math.ceil(p["warps"] / 8)
+        assert p["max_rounds_per_warp"] == math.ceil(p["total_rounds"] / p["warps"])
+        probe = range(p["warps"]) if p["warps"] <= 4096 else list(range(64)) + list(range(p["warps"] - 64, p["warps"]))
+        prev_end, sizes = None, []
+        for w in probe:
+            a, b = pkg.plan_warp_range(p, w)
+            assert a == w * p["total_rounds"] // p["warps"] and b == (w + 1) * p["total_rounds"] // p["warps"]
+            if prev_end is not None and w == prev_w + 1:
+                assert a == prev_end
+            prev_end, prev_w = b, w
+            sizes.append(b - a)
+        assert pkg.plan_warp_range(p, 0)[0] == 0 and pkg.plan_warp_range(p, p["warps"] - 1)[1] == p["total_rounds"]
+        assert max(sizes) - min(sizes) <= 1 and max(sizes) == p["max_rounds_per_warp"] or len(sizes) < p["warps"]
+        with pytest.raises(pkg.Mcb200Error):
+            pkg.plan_warp_range(p, p["warps"])
 
 
 def test_planner_fills_the_machine(pkg):
-    """Few options / many trials must still spread over all resident CTAs; many options need one slice each."""
-    slots = 148 * 8
-    few = pkg.plan_query(1, 252.0, 1e6, slots)
-    assert few["items"] >= 0.8 * slots
-    many = pkg.plan_query(100000, 252.0, 1e4, slots)
-    assert many["slices"] == 1
+    """Any batch shape spreads evenly over all resident warps: the busiest warp is within one round of the mean."""
+    slots = 148 * 4
+    for n, steps, trials in [(1, 252.0, 1e6), (100000, 252.0, 1e4), (112, 100.0, 20000.0), (112, 1000.0, 2000.0),
+                             (4096, 252.0, 1e5)]:
+        p = pkg.plan_query(n, steps, trials, slots)
+        assert p["grid"] == slots
+        mean = p["total_rounds"] / p["warps"]
+        assert p["max_rounds_per_warp"] < mean + 1
     c2 = pkg.plan_query(112, 100.0, 20000.0, slots)
-    ideal = 112 * 20000 / (slots * 256)
-    waves = math.ceil(c2["items"] / slots)
-    assert waves * c2["paths_per_thread"] <= 1.15 * ideal
+    assert c2["max_rounds_per_warp"] / (c2["total_rounds"] / c2["warps"]) < 1.02     # 15 vs 14.8 rounds
+    small = pkg.plan_query(112, 100.0, 1000.0, slots)                                # fewer rounds than warps
+    assert small["warps"] == small["total_rounds"] and small["max_rounds_per_warp"] == 1
+    odd = pkg.plan_query(1, 100.0, 10000.0, slots)                                   # 313 rounds: W not a multiple of 8
+    assert odd["warps"] == 313 and odd["grid"] == 40
 
 
 def test_planner_rejects_bad_requests(pkg):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Instruction mix of the hottest loop of a kernel (by backward branch with the most MUFU in its body).
+"""Instruction mix of the hottest loop of a kernel (the backward branch whose body has the highest MUFU density).
 
     python tools/sass_mix.py <lib.so|cubin> <mangled-name-substring> [pairs_per_iteration]
 
@@ -50,7 +50,7 @@ def main():
                 tgt = int(t.group(1), 16)
                 loop = [x for x in ins if tgt <= x[0] <= addr]
                 mufu = sum(1 for x in loop if x[1].startswith("MUFU"))
-                if best is None or mufu > best[0]:
+                if mufu >= 3 and (best is None or mufu / len(loop) > best[0] / len(best[1])):
                     best = (mufu, loop)
     mufu, loop = best
     ops = Counter(x[1].split(".")[0] + ("." + x[1].split(".")[1] if x[1].startswith(("IMAD.", "MUFU.")) and "." in x[1] else "") for x in loop)
