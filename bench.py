@@ -123,6 +123,18 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the path kernel, from the committed ncu --set full
+    capture of this workload (profiles/r1_ncu_<workload>_v2_summary.json); None when no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_%s_v2_summary.json" % workload)) as f:
+            m = json.load(f)["metrics"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(m[k]["value"] * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -325,7 +337,8 @@ def b200_arm(args, w):
             "config": {"workload": w["name"], "options_per_gpu": n, "trials": w["trials"], "steps_per_path": w["steps"],
                        "outputs": "all Greeks + prices + SE" if greeks else "call + put + SE from one pass",
                        "l2": "flushed between timed steps (256 MiB write, outside the events); kernel reads %d B" % h2d,
-                       "parallelism": "options-major, one process per GPU, substream block = rank",
+                       "parallelism": "options-major, one process per GPU, substream block = rank, no data-path collective",
+                       "launch": "one fused kernel per step: paths + payoffs + deterministic reduce + finalize",
                        "published": "README.md:122 (M1, derived path-steps/s)"},
             "options_per_sec": world * n * args.steps / (ms_total * 1e-3),
             "clocks": clocks,
@@ -333,7 +346,12 @@ def b200_arm(args, w):
                     "ms_per_step": 1e3 * float(te.item()) / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "issue/mufu (not hbm, not tensor: SURVEY 8d)", "achieved": achieved, "peak": peak,
-                         "unit": "path-steps/s", "frac": frac, "traffic": None,
+                         "unit": "path-steps/s", "frac": frac, "traffic": ncu_traffic(args.workload),
+                         "traffic_note": "DRAM bytes per launch (ncu): the per-thread generator states, read once; "
+                                         "path data never leaves registers",
+                         "alu_pipe_ceiling_frac": 3.33 * 2.0 / ROOFLINE_PATH_STEPS_PER_CLK_PER_SM,
+                         "alu_pipe_ceiling_note": "the inner step alone sustains 3.33 pairs/clk/SM on B200 (ALU pipe "
+                                                  "saturated, profiles/r1_microbench_v2_pipes.json): 83% of this peak",
                          "kernel": "simulate_kernel", "kernel_ms": sim_avg_ms, "launches_timed": len(sim_ms),
                          "peak_basis": "%d SMs x %.0f MHz (MEASURED_PEAKS.json sm_max_mhz%s) x 8 path-steps/clk/SM"
                                        % (info0["sm_count"], sm_max_mhz, "" if peaks else ", fallback"),

@@ -61,8 +61,9 @@ int mcb200_ctx_info(mcb200_ctx *ctx, mcb200_info *out);
 
 /* Launch plan for one batch: how the work maps onto the resident warps.  Pure host logic.
  * A "round" is 32 consecutive paths of one option (one per lane).  Round r belongs to option r / rounds_per_option;
- * warp w (global warp index = CTA * 8 + warp in CTA) simulates rounds [w*R/W, (w+1)*R/W), R = total_rounds, W = warps,
- * in order, drawing from the generator substream of global thread 32*w + lane. */
+ * logical warp w simulates rounds [w*R/W, (w+1)*R/W), R = total_rounds, W = warps, in order, and its lane l draws from
+ * generator substream 32*w + l of the pool.  (Hardware warp h of CTA c is logical warp 8c + 2*(h%4) + h/4, so the two
+ * warps of an SM sub-partition own neighbouring ranges.) */
 typedef struct {
     int n_paths;                 /* 8 * floor(num_trials / 8) */
     int half_steps;              /* floor(steps) / 2 */

@@ -207,14 +207,18 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
     __shared__ float s_const[kConstInSmem ? kWarps * kConst : 1];
 
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    // Logical warp index.  Hardware warp h of a CTA runs on SM sub-partition h % 4; giving the two warps of a
+    // sub-partition CONSECUTIVE logical indices keeps the +-1-round differences of the range partition from lining up
+    // with the sub-partitions (with R/W = 1.5 every odd logical warp has the extra round).
+    const int hw = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarps + ((hw & 3) * 2 + (hw >> 2));
     const long long R = a.total_rounds, W = a.n_warps;
     if (w >= a.n_warps) return;                              // tail of the last CTA when W is not a multiple of 8
     long long r = round_begin(w, R, W);
     const long long r_end = round_begin(w + 1, R, W);        // W <= R: never empty
 
     Xoshiro256 g;
-    const size_t gtid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    const size_t gtid = (size_t)w * 32 + lane;              // the generator stream belongs to the LOGICAL thread
     if (STREAM == STREAM_FAST) xoshiro_load(g, a.pool + 4ull * gtid);
 
     float creg[kConstInSmem ? 1 : kConst];
@@ -295,23 +299,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
             prev = __shfl_sync(0xffffffffu, prev, 0);
             if ((int)prev == w_last - w_first) {
                 __threadfence();
+                // Fixed-order sum of the option's segments.  Lane l = (group, accumulator): kGroups groups stride over
+                // the segments with independent loads in flight (a serial walk would expose one L2 round trip per
+                // segment at the very end of the kernel), then the groups are combined by a fixed butterfly.
+                constexpr int kAccPad = kAcc <= 4 ? 4 : (kAcc <= 8 ? 8 : (kAcc <= 16 ? 16 : 32));
+                constexpr int kGroups = 32 / kAccPad;
+                const int i = lane % kAccPad, grp = lane / kAccPad;
+                const int n_seg = w_last - w_first + 1;
                 double s = 0.0;
-                if (w_last - w_first < 64) {
-                    if (lane < kAcc)
-                        for (int ww = w_first; ww <= w_last; ++ww)
-                            s += __ldcg(a.slots + ((size_t)ww + (size_t)o) * kAcc + lane);
-                } else {
-                    // many segments (few options, huge trial counts): lanes stride over the warps, fixed butterfly
-                    for (int i = 0; i < kAcc; ++i) {
-                        double t = 0.0;
-                        for (int ww = w_first + lane; ww <= w_last; ww += 32)
-                            t += __ldcg(a.slots + ((size_t)ww + (size_t)o) * kAcc + i);
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                        t = __shfl_sync(0xffffffffu, t, 0);
-                        if (lane == i) s = t;
+                if (i < kAcc) {
+                    const double* base = a.slots + ((size_t)w_first + (size_t)o) * kAcc + i;
+                    int j = grp;
+                    for (; j + 3 * kGroups < n_seg; j += 4 * kGroups) {
+                        const double v0 = __ldcg(base + (size_t)j * kAcc);
+                        const double v1 = __ldcg(base + (size_t)(j + kGroups) * kAcc);
+                        const double v2 = __ldcg(base + (size_t)(j + 2 * kGroups) * kAcc);
+                        const double v3 = __ldcg(base + (size_t)(j + 3 * kGroups) * kAcc);
+                        s += v0; s += v1; s += v2; s += v3;
                     }
+                    for (; j < n_seg; j += kGroups) s += __ldcg(base + (size_t)j * kAcc);
                 }
+#pragma unroll
+                for (int off = kAccPad; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
                 if (a.moments_out && lane < kAcc) a.moments_out[(size_t)o * kAcc + lane] = s;
                 if (a.finalize) {
                     const double sum = __shfl_sync(0xffffffffu, s, (2 * lane) & 31);

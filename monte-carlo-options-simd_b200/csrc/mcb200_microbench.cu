@@ -76,7 +76,7 @@ struct Bench {
 
 // Times the second of two launches; rate = ops_per_thread * threads resident per SM / cycles of the slowest CTA.
 template <typename Launch>
-static void timed(Bench& b, const char* name, int ctas_per_sm, double ops_per_thread, Launch launch) {
+static void timed(Bench& b, const char* name, int ctas_per_sm, double ops_per_thread, Launch launch, int threads = kThreads) {
     if (b.rc != 0 || b.n >= b.cap) return;
     const int grid = b.sm_count * ctas_per_sm;
     cudaEvent_t e0, e1;
@@ -96,7 +96,7 @@ static void timed(Bench& b, const char* name, int ctas_per_sm, double ops_per_th
     std::memset(o, 0, sizeof(*o));
     std::snprintf(o->name, sizeof(o->name), "%s", name);
     // warps finish at different times under the greedy scheduler: the slowest CTA bounds the sustained rate
-    o->ops_per_clk_per_sm = ops_per_thread * kThreads * ctas_per_sm / (double)max_cycles;
+    o->ops_per_clk_per_sm = ops_per_thread * threads * ctas_per_sm / (double)max_cycles;
     o->elapsed_ms = ms;
     o->sm_clock_mhz = (double)max_cycles / (ms * 1e3);
 }
@@ -147,12 +147,11 @@ __global__ void __launch_bounds__(kThreads, 8) pair_kernel(uint32_t* sink, long 
 
 // ctas_per_sm < 8 is forced with dynamic shared memory (the kernel itself always fits 8 CTAs of 256 threads per SM).
 template <int V, int FMODE, bool GEN_ONLY, int UNROLL, int EXTRA>
-static void run_pair(Bench& b, int ctas_per_sm = 8) {
-    char name[32];
+static void run_pair(Bench& b, int ctas_per_sm = 8, int threads = kThreads) {
+    char name[32], occ[16] = "";
+    if (ctas_per_sm != 8 || threads != kThreads) std::snprintf(occ, sizeof(occ), "_w%d", ctas_per_sm * threads / 32);
     std::snprintf(name, sizeof(name), "%s_xo%d_f%d_u%d%s%s", GEN_ONLY ? "gen" : "pair", V, FMODE, UNROLL,
-                  EXTRA == 1 ? "+4ffma" : EXTRA == 2 ? "+2lop3" : EXTRA == 3 ? "+2imad" : EXTRA == 4 ? "+2wide" : "",
-                  ctas_per_sm == 8 ? "" : ctas_per_sm == 7 ? "_occ7" : ctas_per_sm == 6 ? "_occ6" : ctas_per_sm == 5 ? "_occ5" :
-                  ctas_per_sm == 4 ? "_occ4" : ctas_per_sm == 3 ? "_occ3" : "_occ2");
+                  EXTRA == 1 ? "+4ffma" : EXTRA == 2 ? "+2lop3" : EXTRA == 3 ? "+2imad" : EXTRA == 4 ? "+2wide" : "", occ);
     auto kern = pair_kernel<V, FMODE, GEN_ONLY, UNROLL, EXTRA>;
     size_t smem = 0;
     if (ctas_per_sm < 8) {
@@ -160,8 +159,8 @@ static void run_pair(Bench& b, int ctas_per_sm = 8) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { b.rc = -1; return; }
     }
     timed(b, name, ctas_per_sm, (double)kPairIters, [&](int grid, uint32_t seed) {
-        kern<<<grid, kThreads, smem, b.st>>>(b.d_sink, b.d_cycles, seed);
-    });
+        kern<<<grid, threads, smem, b.st>>>(b.d_sink, b.d_cycles, seed);
+    }, threads);
 }
 
 #define MIX8(a, b, c, d, e, f, g, h) ((unsigned)(a) << 28 | (b) << 24 | (c) << 20 | (d) << 16 | (e) << 12 | (f) << 8 | (g) << 4 | (h))
@@ -197,6 +196,9 @@ int run_microbench(cudaStream_t st, int sm_count, mcb200_pipe_rate* out, int cap
     run_pair<0, 0, false, 4, 0>(b, 7); run_pair<0, 0, false, 4, 0>(b, 6); run_pair<0, 0, false, 4, 0>(b, 5);
     run_pair<0, 0, false, 4, 0>(b, 4); run_pair<0, 0, false, 4, 0>(b, 3); run_pair<0, 0, false, 4, 0>(b, 2);
     run_pair<0, 0, false, 8, 0>(b, 4); run_pair<0, 0, false, 8, 0>(b, 2);
+    // few warps per SM (named by resident warps per SM): how much of the pipe can 1 or 2 warps per sub-partition use?
+    run_pair<0, 0, false, 8, 0>(b, 1, 256); run_pair<0, 0, false, 8, 0>(b, 1, 128); run_pair<0, 0, false, 4, 0>(b, 1, 128);
+    run_pair<0, 0, false, 8, 0>(b, 1, 32);
     cudaFree(b.d_sink); cudaFree(b.d_cycles);
     return b.rc == 0 ? b.n : -1;
 }

@@ -1,0 +1,71 @@
+"""torchrun worker for tests/test_multigpu.py: one process per GPU, NCCL.  Prints one JSON line from rank 0."""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GRID = dict(strike=110.0, vol=0.25, r=0.05, t=0.5, q=0.02)
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("monte-carlo-options-simd_b200")
+    sh = pkg.sharding
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- options-major: each rank prices its contiguous block on its own long_jump substream block, no collective on
+    #      the data path; the blocks are gathered only to be checked
+    spots = np.arange(50, 162, dtype=np.float32)
+    lo, hi = sh.partition_options(len(spots), world, rank)
+    with pkg.Context(device=local, seed=77, substream_block=rank) as ctx:
+        res = ctx.price_batch(spots[lo:hi], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 20000.0)
+        again = ctx.price_batch(spots[lo:hi], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 20000.0)
+        ctx.set_seed(77, rank)
+        replay = ctx.price_batch(spots[lo:hi], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 20000.0)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, dict(lo=lo, hi=hi, call=res["call"].tolist(), call_se=res["call_se"].tolist(),
+                                        put=res["put"].tolist(), put_se=res["put_se"].tolist(),
+                                        replay_equal=bool(np.array_equal(res["call"], replay["call"])),
+                                        fresh_differs=bool(not np.array_equal(res["call"], again["call"]))))
+    out["options_major"] = blocks
+
+    # ---- trials-minor: every rank simulates a disjoint trial range of the SAME options; the fp64 moment sums are
+    #      all-reduced over NCCL and finalised once (results land on every rank)
+    tspots = torch.tensor([90.0, 100.0, 110.0, 120.0, 130.0], dtype=torch.float32, device=dev)
+    n = tspots.numel()
+    cols = [tspots] + [torch.full((n,), v, dtype=torch.float32, device=dev) for v in
+                       (GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])]
+    ptrs = [c.data_ptr() for c in cols]
+    trials = 400000.0
+    local_trials, total_paths = sh.partition_trials(trials, world, rank)
+    mom = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+    vals = torch.zeros(4, n, dtype=torch.float32, device=dev)
+    with pkg.Context(device=local, seed=99, substream_block=rank) as ctx:
+        ctx.price_moments_device(n, ptrs, 100.0, float(local_trials), mom.data_ptr(), stream=stream)
+        sh.combine_moments(mom)                         # ncclAllReduce(fp64, sum) on the same stream
+        ctx.price_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), mom.data_ptr(), float(total_paths), trials,
+                                  [vals[i].data_ptr() for i in range(4)], stream=stream)
+        torch.cuda.synchronize()
+    gathered = [torch.zeros_like(vals) for _ in range(world)]
+    dist.all_gather(gathered, vals)
+    out["trials_minor"] = dict(call=vals[0].tolist(), put=vals[1].tolist(), call_se=vals[2].tolist(),
+                               put_se=vals[3].tolist(), spots=tspots.tolist(), total_paths=total_paths,
+                               same_on_all_ranks=all(bool(torch.equal(g, vals)) for g in gathered))
+    if rank == 0:
+        print("MULTIGPU_JSON " + json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
