@@ -192,6 +192,7 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 //   * work unit = a "round": 32 consecutive paths of one option, one path per lane.  The n_options * ceil(n_paths/32)
 //     rounds are dealt to the resident warps in contiguous, equal (+-1) ranges, so every SM sub-partition gets the same
 //     load whatever the batch shape (no CTA-level quantisation, no block barrier anywhere in the path loop);
+//   * the inner step is quad_fast(): three xoshiro256++ outputs feed four Box-Muller pairs (mcb200_pair.cuh);
 //   * every thread owns one generator stream for the whole launch (state loaded from / stored back to the pool, so
 //     consecutive launches continue the same substreams) and keeps its fp32 moment sums in registers;
 //   * when a warp leaves an option it reduces its sums (fp64, butterfly) into slot (warp + option) and bumps the
@@ -259,8 +260,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 }
                 float m = 0.0f;
                 if (STREAM == STREAM_FAST) {
-#pragma unroll 8
-                    for (int i = 0; i < a.half_steps; ++i) m = pair_fast(g, m);
+                    // four pairs per three generator outputs, then the 0..3 left-over pairs one output each
+                    const int quads = a.half_steps >> 2;
+#pragma unroll 2
+                    for (int i = 0; i < quads; ++i) m = quad_fast(g, m);
+                    for (int i = quads << 2; i < a.half_steps; ++i) m = pair_fast(g, m);
                 } else {
 #pragma unroll 2
                     for (int i = 0; i < a.half_steps; ++i) m = pair_ref(g, m);

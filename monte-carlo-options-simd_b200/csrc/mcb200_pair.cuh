@@ -84,6 +84,36 @@ __device__ __forceinline__ float pair_fast(Xoshiro256& g, float acc) {
     return pair_fast_v<kXoVariant, kFloatMode>(g, acc);
 }
 
+// Dense use of the generator: THREE 64-bit outputs -> FOUR Box-Muller pairs (eight time steps).
+//   words w0..w5 = (hi, lo) of the three outputs.  Pairs A, B, C take the top 23 bits of (w0,w1), (w2,w3), (w4,w5) like
+//   pair_fast.  Pair D is built from the six low BYTES, which pair_fast throws away: u1 from the low bytes of
+//   w0, w2, w4 and the angle from those of w1, w3, w5 (two PRMT byte gathers + one LEA.HI each; bit 8 of every word
+//   and one bit of each gathered field stay unused).  No bit is used twice, every field is 23 uniform bits, and the
+//   generator -- 15 of the 17 ALU-pipe instructions of a pair, the binding resource -- runs 3/4 as often.
+__device__ __forceinline__ float bm_term(uint32_t b1, uint32_t b2, float acc) {
+    const float u1 = 2.0f - __uint_as_float(b1);                    // b1, b2: bit patterns of floats in [1,2)
+    const float rad = mufu_sqrt(fabsf(mufu_lg2(u1)));
+    const float ang = fmaf(__uint_as_float(b2), kTwoPi, kQuarterPi);
+    return fmaf(rad, mufu_sin(ang), acc);
+}
+__device__ __forceinline__ uint32_t top23(uint32_t w) { return (w >> 9) | 0x3f800000u; }
+__device__ __forceinline__ uint32_t low_bytes23(uint32_t wa, uint32_t wb, uint32_t wc) {
+    uint32_t t, x;
+    asm("prmt.b32 %0, %1, %2, 0x4400;" : "=r"(t) : "r"(wa), "r"(wb));       // t = [ . , wb.b0, wa.b0, . ]
+    asm("prmt.b32 %0, %1, %2, 0x4210;" : "=r"(x) : "r"(t), "r"(wc));        // x = [wc.b0, wb.b0, wa.b0, . ]
+    return top23(x);
+}
+__device__ __forceinline__ float quad_fast(Xoshiro256& g, float acc) {
+    uint32_t w0, w1, w2, w3, w4, w5;
+    xoshiro_next(g, w0, w1);
+    xoshiro_next(g, w2, w3);
+    xoshiro_next(g, w4, w5);
+    acc = bm_term(top23(w0), top23(w1), acc);
+    acc = bm_term(top23(w2), top23(w3), acc);
+    acc = bm_term(top23(w4), top23(w5), acc);
+    return bm_term(low_bytes23(w0, w2, w4), low_bytes23(w1, w3, w5), acc);
+}
+
 // Reference-stream pair update: consumes the generator exactly like rand32x8.rs:5-21 + mc_simd.rs:9-21
 // (two 64-bit outputs, top 53 bits -> f64 -> f32) and evaluates the reference's formula with MUFU math.
 __device__ __forceinline__ float u53_to_f32(uint32_t hi, uint32_t lo) {

@@ -6,6 +6,10 @@
  * The production kernel keeps that estimator but restates it for the GPU's MUFU/ALU pipes:
  *     sqrt(-ln u1) (sin t + cos t)  ==  sqrt(2 ln 2) * sqrt(-log2 u1) * sin(t + pi/4)         (exact identity)
  * and draws u1,u2 from ONE 64-bit output (high word -> u1 in (0,1], low word -> the angle), 23 bits each.
+ * Pairs are taken four at a time from THREE outputs (quad_fast in mcb200_pair.cuh): pairs A, B, C use the top 23 bits
+ * of the words of outputs 0, 1, 2; pair D uses the six low bytes those leave over (u1 from the low bytes of the three
+ * high words, the angle from those of the three low words; the byte of the LAST output is the most significant).
+ * The 0..3 pairs left when half_steps is not a multiple of 4 use one output each.
  * The constant sqrt(2 ln 2) is folded into the terminal scale.  This file states that convention on the CPU with
  * libm (log2f / sqrtf / sinf / exp2f); the GPU differs only by the MUFU approximations (tests give the tolerance).
  *
@@ -19,16 +23,36 @@
 
 static inline float bits_to_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 
-/* one Box-Muller pair in the fast convention: returns sqrt(|log2 u1|) * sin(2*pi*f2 + pi/4) added to acc */
-static inline float fast_pair_increment(xo256_t *g, float acc) {
-    const uint64_t x = xo256pp_next(g);
-    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
-    const float f1 = bits_to_float((hi >> 9) | 0x3f800000u);     /* [1,2) */
-    const float f2 = bits_to_float((lo >> 9) | 0x3f800000u);     /* [1,2): one full turn */
+/* one Box-Muller term from the bit patterns of two floats in [1,2): sqrt(|log2 u1|) * sin(2*pi*f2 + pi/4) + acc */
+static inline float bm_term(uint32_t b1, uint32_t b2, float acc) {
+    const float f1 = bits_to_float(b1), f2 = bits_to_float(b2);
     const float u1 = 2.0f - f1;                                  /* (0,1], exact */
     const float rad = sqrtf(fabsf(log2f(u1)));
     const float ang = fmaf(f2, 6.28318530717958647692f, 0.78539816339744830962f);
     return fmaf(rad, sinf(ang), acc);
+}
+static inline uint32_t top23(uint32_t w) { return (w >> 9) | 0x3f800000u; }
+/* 23 bits from the low bytes of three words: wc's byte is the most significant, then wb's, then wa's top 7 bits */
+static inline uint32_t low_bytes23(uint32_t wa, uint32_t wb, uint32_t wc) {
+    const uint32_t x = ((wc & 0xffu) << 24) | ((wb & 0xffu) << 16) | ((wa & 0xffu) << 8);
+    return top23(x);
+}
+
+/* one pair from one output (the left-over pairs of a path) */
+static inline float fast_pair_increment(xo256_t *g, float acc) {
+    const uint64_t x = xo256pp_next(g);
+    return bm_term(top23((uint32_t)(x >> 32)), top23((uint32_t)x), acc);
+}
+
+/* four pairs from three outputs */
+static inline float fast_quad_increment(xo256_t *g, float acc) {
+    const uint64_t x0 = xo256pp_next(g), x1 = xo256pp_next(g), x2 = xo256pp_next(g);
+    const uint32_t w0 = (uint32_t)(x0 >> 32), w1 = (uint32_t)x0, w2 = (uint32_t)(x1 >> 32), w3 = (uint32_t)x1;
+    const uint32_t w4 = (uint32_t)(x2 >> 32), w5 = (uint32_t)x2;
+    acc = bm_term(top23(w0), top23(w1), acc);
+    acc = bm_term(top23(w2), top23(w3), acc);
+    acc = bm_term(top23(w4), top23(w5), acc);
+    return bm_term(low_bytes23(w0, w2, w4), low_bytes23(w1, w3, w5), acc);
 }
 
 /* Run `n_paths` consecutive paths of `half_steps` pairs each from one stream.  state is advanced in place.
@@ -37,7 +61,9 @@ void fast_model_stream_paths(uint64_t state[4], int half_steps, int n_paths, flo
     xo256_t g; memcpy(g.s, state, 32);
     for (int p = 0; p < n_paths; p++) {
         float acc = 0.0f;
-        for (int i = 0; i < half_steps; i++) acc = fast_pair_increment(&g, acc);
+        const int quads = half_steps / 4;
+        for (int i = 0; i < quads; i++) acc = fast_quad_increment(&g, acc);
+        for (int i = 4 * quads; i < half_steps; i++) acc = fast_pair_increment(&g, acc);
         out_m[p] = acc;
     }
     memcpy(state, g.s, 32);
