@@ -125,9 +125,9 @@ class ClockSampler:
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the path kernel, from the committed ncu --set full
-    capture of this workload (profiles/r1_ncu_<workload>_v2_summary.json); None when no capture exists."""
+    capture of this workload (profiles/r1_ncu_<workload>_v3_summary.json); None when no capture exists."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_%s_v2_summary.json" % workload)) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_%s_v3_summary.json" % workload)) as f:
             m = json.load(f)["metrics"]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         return sum(m[k]["value"] * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
