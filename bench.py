@@ -245,10 +245,13 @@ def b200_arm(args, w):
             ctx.price_batch_device(n, in_ptrs, w["steps"], w["trials"], [out_d[i].data_ptr() for i in range(4)],
                                    antithetic=w["av"], stream=stream)
 
+    # e2e: one public C-ABI call per step on HOST buffers (mcb200_price_batch / mcb200_greeks_batch); the ctypes
+    # marshalling of the pointers is done once, the call itself copies in, launches, copies out and synchronizes
+    prepared = (ctx.prepare_greeks_batch(*cols_h, w["steps"], w["trials"], *bumps) if greeks else
+                ctx.prepare_price_batch(*cols_h, w["steps"], w["trials"], antithetic=w["av"]))
+
     def step_host():
-        if greeks:
-            return ctx.greeks_batch(*cols_h, w["steps"], w["trials"], *bumps)
-        return ctx.price_batch(*cols_h, w["steps"], w["trials"], antithetic=w["av"])
+        return prepared.run()
 
     def barrier():
         if world > 1:

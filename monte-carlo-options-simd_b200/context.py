@@ -99,6 +99,32 @@ class Context:
         res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
         return res
 
+    def prepare_price_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                            num_trials, antithetic=False):
+        """Bind host buffers once for repeated pricing of the same batch shape: returns a PreparedCall whose run()
+        is exactly one mcb200_price_batch() C-ABI call (inputs are re-read from the bound arrays on every run, results
+        land in .out['call' | 'put' | 'call_se' | 'put_se'])."""
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        args = (self._h, n, *[N.fptr(a) for a in arrs], C.c_float(steps), C.c_float(num_trials),
+                N.ANTITHETIC if antithetic else 0, *[N.fptr(o) for o in out])
+        return PreparedCall(N.lib().mcb200_price_batch, args, arrs,
+                            dict(call=out[0], put=out[1], call_se=out[2], put_se=out[3]))
+
+    def prepare_greeks_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                             num_trials, delta_spot=0.01, delta_volatility=0.01, delta_risk_free_rate=0.01,
+                             delta_years_to_expiry=0.001):
+        """Like prepare_price_batch for mcb200_greeks_batch(); results in .out[name] and .out[name + '_se']."""
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        vals = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        ses = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        bumps = N.Bumps(delta_spot, delta_volatility, delta_risk_free_rate, delta_years_to_expiry)
+        args = (self._h, n, *[N.fptr(a) for a in arrs], C.c_float(steps), C.c_float(num_trials), C.byref(bumps),
+                N._GreekOut(*[N.fptr(v) for v in vals]), N._GreekOut(*[N.fptr(s) for s in ses]))
+        res = {name: vals[i] for i, name in enumerate(N.GREEK_NAMES)}
+        res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
+        return PreparedCall(N.lib().mcb200_greeks_batch, args, arrs + [bumps], res)
+
     # ------------------------------------------------------------------ parity / inspection modes
     def price_batch_refstream(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
                               num_trials, chunk_seeds, antithetic=False, want_growth=False):
@@ -167,6 +193,17 @@ class Context:
                                                      C.c_void_p(moments_ptr), float(total_paths),
                                                      float(total_num_trials), *[C.c_void_p(p) for p in out_ptrs],
                                                      C.c_void_p(stream)))
+
+
+class PreparedCall:
+    """A C-ABI call with its host buffers bound (the ctypes marshalling is done once, not per call)."""
+
+    def __init__(self, fn, args, keep, out):
+        self._fn, self._args, self._keep, self.out = fn, args, keep, out
+
+    def run(self):
+        N.check(self._fn(*self._args))
+        return self.out
 
 
 def plan_query(n_options, steps, num_trials, grid_slots):

@@ -83,7 +83,8 @@ struct mcb200_ctx {
     double* slots = nullptr; size_t slots_cap = 0;            // doubles: per (warp, option) partial moment sums
     unsigned* arrivals = nullptr; size_t arrivals_cap = 0;    // per-option arrival counters, zero between launches
     double* moments = nullptr; size_t moments_cap = 0;        // doubles (only for the zero-path corner)
-    float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned host / device)
+    float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned+mapped host / device)
+    float* h_stage_dev = nullptr;  // device-side address of h_stage: small batches write their results straight to it
     uint64_t launches = 0;
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -116,9 +117,10 @@ static int ensure_stage(mcb200_ctx* c, size_t need_floats) {
     if (c->stage_cap >= need_floats) return MCB200_OK;
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
-    c->h_stage = nullptr; c->d_stage = nullptr; c->stage_cap = 0;
+    c->h_stage = nullptr; c->d_stage = nullptr; c->h_stage_dev = nullptr; c->stage_cap = 0;
     size_t want = need_floats + need_floats / 2 + 4096;
-    CU(cudaHostAlloc((void**)&c->h_stage, want * sizeof(float), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&c->h_stage, want * sizeof(float), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&c->h_stage_dev, c->h_stage, 0));
     CU(cudaMalloc((void**)&c->d_stage, want * sizeof(float)));
     c->stage_cap = want;
     return MCB200_OK;
@@ -237,6 +239,8 @@ struct Request {
     Bumps bumps{1.0f, 1.0f, 1.0f, 1.0f};
     const uint64_t* chunk_seeds = nullptr;   // device
     float* growth_out = nullptr;             // device
+    bool use_inline = false;                 // n == 1 host call: inputs travel in the launch parameters
+    float inline_opt[6] = {0, 0, 0, 0, 0, 0};
 };
 
 template <int STREAM, int PAYOFF, bool DUMP>
@@ -300,6 +304,11 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.moments_out = moments_out; a.finalize = finalize ? 1 : 0;
     a.fin = make_finalize(n_est, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out, out_se);
     a.growth_out = rq.growth_out;
+    if (rq.use_inline) {
+        a.use_inline = 1; a.fin.use_inline = 1;
+        for (int k = 0; k < 6; ++k) a.inline_opt[k] = rq.inline_opt[k];
+        a.fin.inline_rate = rq.inline_opt[3]; a.fin.inline_years = rq.inline_opt[4];
+    }
     const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     switch (key) {
@@ -407,6 +416,7 @@ extern "C" int mcb200_price_finalize_device(mcb200_ctx* c, int n, const float* r
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer entry points
+constexpr int kDirectWriteMaxOptions = 4096;
 // Staging layout (floats): [6][n] inputs | [2*n_est][n] outputs (value rows then SE rows).
 static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps, float num_trials, int payoff,
                     int stream_mode, Bumps bumps, const uint8_t* chunk_seeds_host, float* const* out,
@@ -422,12 +432,22 @@ static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps,
     const int n_est = payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
     const size_t in_f = 6 * (size_t)n, out_f = 2 * (size_t)n_est * n;
     if ((rc = ensure_stage(c, in_f + out_f))) return rc;
-    for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
     cudaStream_t st = c->stream;
-    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
     Request rq;
     rq.n = n; rq.steps = steps; rq.num_trials = num_trials; rq.payoff = payoff; rq.stream_mode = stream_mode;
     rq.bumps = bumps; rq.dump = dump;
+    // Small batches skip the copy engines: a single option carries its six inputs in the launch parameters, and up to
+    // kDirectWriteMaxOptions options have their results written by the kernel straight into the mapped pinned staging
+    // buffer (posted PCIe writes).  One launch + one stream synchronize is then the whole call.
+    const bool inline_in = (n == 1 && pl.n_paths > 0);
+    const bool direct_out = (n <= kDirectWriteMaxOptions);
+    if (inline_in) {
+        rq.use_inline = true;
+        for (int k = 0; k < 6; ++k) rq.inline_opt[k] = in[k][0];
+    } else {
+        for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
+        CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
+    }
     const float* d = c->d_stage;
     rq.opt = OptionArrays{d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n};
     uint64_t* d_seeds = nullptr; float* d_growth = nullptr;
@@ -447,13 +467,16 @@ static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps,
         rq.growth_out = d_growth;
     }
     float* d_out[EST_COUNT_GREEKS]; float* d_se[EST_COUNT_GREEKS];
+    float* out_base = (direct_out ? c->h_stage_dev : c->d_stage) + in_f;
     for (int e = 0; e < n_est; ++e) {
-        d_out[e] = c->d_stage + in_f + (size_t)e * n;
-        d_se[e] = c->d_stage + in_f + (size_t)(n_est + e) * n;
+        d_out[e] = out_base + (size_t)e * n;
+        d_se[e] = out_base + (size_t)(n_est + e) * n;
     }
     rc = run_device(c, rq, d_out, d_se, st);
     if (rc == MCB200_OK) {
-        cudaError_t e = cudaMemcpyAsync(c->h_stage + in_f, c->d_stage + in_f, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaSuccess;
+        if (!direct_out)
+            e = cudaMemcpyAsync(c->h_stage + in_f, c->d_stage + in_f, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && dump && growth_bytes)
             e = cudaMemcpyAsync(growth_out_host, d_growth, growth_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

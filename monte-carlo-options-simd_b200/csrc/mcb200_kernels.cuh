@@ -39,6 +39,7 @@ struct FinalizeSpec {       // how per-option moment sums become prices / Greeks
     double n_paths;          // paths simulated in total (all shards)
     double num_trials;       // divisor, as passed by the caller (mc_simd.rs:77 divides by num_trials)
     const float* rate; const float* years;
+    int use_inline; float inline_rate, inline_years;   // single-option calls carry their inputs in the launch parameters
     Bumps bumps;
     float* out[EST_COUNT_GREEKS];      // estimator values (nullable)
     float* out_se[EST_COUNT_GREEKS];   // their standard errors (nullable)
@@ -62,6 +63,8 @@ struct SimArgs {
     int finalize;            // non-zero: the last warp to finish an option also writes fin.out / fin.out_se
     FinalizeSpec fin;
     float* growth_out;       // DUMP only: [n_options][n_paths] terminal growth factors S_T / spot
+    int use_inline;          // n_options == 1 from a host call: the six inputs ride in the launch parameters (no H2D copy)
+    float inline_opt[6];     // spot, strike, vol, rate, years, div
 };
 
 // f32 constants exactly as the reference computes them (mc_simd.rs:36-45), then rescaled to base-2 exponent units.
@@ -86,8 +89,14 @@ __device__ __forceinline__ LegConst leg_constants(float vol, float rate, float d
 //              [13..16]= c2,d2 for T+h ; c2,d2 for T-h    [17,18] = exp(-r(T+h)), exp(-r(T-h))
 template <int STREAM, int PAYOFF>
 __device__ __forceinline__ void load_option_constants(const SimArgs& a, int o, float* sc) {
-    const float spot = a.opt.spot[o], strike = a.opt.strike[o], vol = a.opt.vol[o];
-    const float rate = a.opt.rate[o], years = a.opt.years[o], div = a.opt.div[o];
+    float spot, strike, vol, rate, years, div;
+    if (a.use_inline) {
+        spot = a.inline_opt[0]; strike = a.inline_opt[1]; vol = a.inline_opt[2];
+        rate = a.inline_opt[3]; years = a.inline_opt[4]; div = a.inline_opt[5];
+    } else {
+        spot = a.opt.spot[o]; strike = a.opt.strike[o]; vol = a.opt.vol[o];
+        rate = a.opt.rate[o]; years = a.opt.years[o]; div = a.opt.div[o];
+    }
     const LegConst base = leg_constants<STREAM>(vol, rate, div, years / a.steps, a.steps);
     sc[0] = spot; sc[1] = strike; sc[2] = base.c2; sc[3] = base.d2;
     if (PAYOFF == PAYOFF_GREEKS) {
@@ -157,7 +166,8 @@ __device__ __forceinline__ float evaluate_path(float m, const float* sc, float (
 // ------------------------------------------------------------------------------------------------ finalisation
 // mean = sum / num_trials * scale ; se = sample std of the per-path estimator / sqrt(n) * (n / num_trials) * scale
 __device__ __forceinline__ void finalize_estimator(const FinalizeSpec& f, int o, int e, double s, double ss) {
-    const float disc = expf(-f.rate[o] * f.years[o]);             // mc_simd.rs:77
+    const float disc = f.use_inline ? expf(-f.inline_rate * f.inline_years)
+                                    : expf(-f.rate[o] * f.years[o]);                      // mc_simd.rs:77
     double scale;
     switch (e) {
         case EST_CALL: case EST_PUT: scale = disc; break;
