@@ -119,6 +119,17 @@ int mcb200_price_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free_
                                  const double *moments, double total_paths, double total_num_trials,
                                  float *call_out, float *put_out, float *call_se, float *put_se, void *cuda_stream);
 
+/* ------------------------------------------------------------------ closed form (analytic companion) ----------- */
+/* Black-Scholes closed form with dividend yield for a batch -- the analytic value the reference's tests compare every
+ * Monte Carlo estimate with (src/bs.rs:42-184, pub(crate) there).  Same units as bs.rs and as the estimators above:
+ * vega and rho per 1 point, theta per year.  out[] in the order of mcb200_greeks_batch; entries may be NULL. */
+int mcb200_bs_batch(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                    const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                    float *const out[MCB200_N_GREEK_OUTPUTS]);
+int mcb200_bs_batch_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                           const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                           float *const out[MCB200_N_GREEK_OUTPUTS], void *cuda_stream);
+
 /* ------------------------------------------------------------------ parity / inspection ------------------------ */
 /* Reference-stream mode: consume the generator exactly like the reference (a 256-byte simd_rand seed per 8-path
  * chunk, two 64-bit outputs per Box-Muller pair, 53-bit -> f64 -> f32 uniforms; rand32x8.rs:5-21, mc_simd.rs:9-21).

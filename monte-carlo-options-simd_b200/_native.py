@@ -93,6 +93,10 @@ def lib():
     L.mcb200_price_moments_device.argtypes = [_vp, C.c_int] + [_vp] * 6 + [_f, _f, C.c_uint, _vp, _vp]
     L.mcb200_price_finalize_device.restype = C.c_int
     L.mcb200_price_finalize_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double] + [_vp] * 4 + [_vp]
+    L.mcb200_bs_batch.restype = C.c_int
+    L.mcb200_bs_batch.argtypes = [_vp, C.c_int] + six + [_GreekOut]
+    L.mcb200_bs_batch_device.restype = C.c_int
+    L.mcb200_bs_batch_device.argtypes = [_vp, C.c_int] + [_vp] * 6 + [_VoidOut, _vp]
     L.mcb200_price_batch_refstream.restype = C.c_int
     L.mcb200_price_batch_refstream.argtypes = ([_vp, C.c_int] + six + [_f, _f, C.c_uint, C.POINTER(C.c_uint8)]
                                                + [_fp] * 5)

@@ -99,6 +99,27 @@ class Context:
         res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
         return res
 
+    def bs_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield):
+        """Black-Scholes closed form for the batch (the reference's analytic oracle, src/bs.rs), computed on the GPU:
+        dict with the ten names of greeks_batch."""
+        n, arrs = self._inputs(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        vals = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        N.check(N.lib().mcb200_bs_batch(self._h, n, *[N.fptr(a) for a in arrs], N._GreekOut(*[N.fptr(v) for v in vals])))
+        return {name: vals[i] for i, name in enumerate(N.GREEK_NAMES)}
+
+    def greeks_batch_with_z(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                            num_trials, **bumps):
+        """greeks_batch plus, per estimator, the closed-form value (name + '_bs') and the z-score
+        (estimate - closed form) / standard error (name + '_z'; NaN where the sample SE is zero)."""
+        res = self.greeks_batch(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
+                                num_trials, **bumps)
+        exact = self.bs_batch(spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield)
+        for name in N.GREEK_NAMES:
+            res[name + "_bs"] = exact[name]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                res[name + "_z"] = np.where(res[name + "_se"] > 0, (res[name] - exact[name]) / res[name + "_se"], np.nan)
+        return res
+
     def prepare_price_batch(self, spot, strike, volatility, risk_free_rate, years_to_expiry, dividend_yield, steps,
                             num_trials, antithetic=False):
         """Bind host buffers once for repeated pricing of the same batch shape: returns a PreparedCall whose run()

@@ -552,6 +552,57 @@ extern "C" int mcb200_price_batch_dump(mcb200_ctx* c, int n, const float* spot, 
                     Bumps{1, 1, 1, 1}, nullptr, out, se, growth_out, true);
 }
 
+// ------------------------------------------------------------------------------------------------ closed form
+static int launch_bs(mcb200_ctx* c, int n, OptionArrays opt, float* const* out, cudaStream_t st) {
+    BsArgs a{};
+    a.opt = opt; a.n = n;
+    for (int e = 0; e < EST_COUNT_GREEKS; ++e) a.out[e] = out ? out[e] : nullptr;
+    bs_closed_form_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_bs_batch_device(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                                      const float* rate, const float* years, const float* div,
+                                      float* const out[MCB200_N_GREEK_OUTPUTS], void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (n == 0) return MCB200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return launch_bs(c, n, OptionArrays{spot, strike, vol, rate, years, div}, out,
+                     cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+extern "C" int mcb200_bs_batch(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                               const float* rate, const float* years, const float* div,
+                               float* const out[MCB200_N_GREEK_OUTPUTS]) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (n == 0) return MCB200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const size_t in_f = 6 * (size_t)n, out_f = (size_t)MCB200_N_GREEK_OUTPUTS * n;
+    if ((rc = ensure_stage(c, in_f + out_f))) return rc;
+    for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
+    const float* d = c->d_stage;
+    float* d_out[MCB200_N_GREEK_OUTPUTS];
+    for (int e = 0; e < MCB200_N_GREEK_OUTPUTS; ++e) d_out[e] = c->d_stage + in_f + (size_t)e * n;
+    rc = launch_bs(c, n, OptionArrays{d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n},
+                   d_out, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_stage + in_f, c->d_stage + in_f, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int e = 0; e < MCB200_N_GREEK_OUTPUTS; ++e)
+        if (out && out[e]) std::memcpy(out[e], c->h_stage + in_f + (size_t)e * n, sizeof(float) * n);
+    return MCB200_OK;
+}
+
 extern "C" int mcb200_ctx_export_states(mcb200_ctx* c, int64_t first, int64_t count, uint64_t* states_out) {
     if (!c || !states_out) return fail(MCB200_ERR_INVALID, "null argument");
     if (first < 0 || count < 0 || first + count > c->pool_threads)

@@ -350,6 +350,45 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
     if (STREAM == STREAM_FAST) xoshiro_store(g, a.pool + 4ull * gtid);
 }
 
+// ------------------------------------------------------------------------------------------------ closed form
+// Black-Scholes with continuous dividend yield for a whole batch: the analytic value every reference test compares a
+// Monte Carlo estimate with (/root/reference/src/bs.rs:42-184; units as there: vega and rho per 1 point, theta per
+// year).  Evaluated in fp64 with erfc (bs.rs uses an f32 Abramowitz-Stegun erf; the difference is below 1e-6 relative),
+// so batched results can be turned into z-scores on the device.  out[e] (nullable) in Estimator order.
+struct BsArgs {
+    OptionArrays opt;
+    int n;
+    float* out[EST_COUNT_GREEKS];
+};
+
+__global__ void bs_closed_form_kernel(const BsArgs a) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.n) return;
+    const double s = a.opt.spot[o], k = a.opt.strike[o], v = a.opt.vol[o];
+    const double r = a.opt.rate[o], t = a.opt.years[o], q = a.opt.div[o];
+    const double sq = sqrt(t), vs = v * sq;
+    const double d1 = (log(s / k) + (r - q + 0.5 * v * v) * t) / vs, d2 = d1 - vs;
+    const double nd1 = 0.5 * erfc(-d1 * 0.70710678118654752440), nd2 = 0.5 * erfc(-d2 * 0.70710678118654752440);
+    const double md1 = 0.5 * erfc(d1 * 0.70710678118654752440), md2 = 0.5 * erfc(d2 * 0.70710678118654752440);   // N(-d)
+    const double pdf = exp(-0.5 * d1 * d1) * 0.39894228040143267794;
+    const double eq = exp(-q * t), er = exp(-r * t);
+    const double decay = -eq * s * pdf * v / (2.0 * sq);
+    double val[EST_COUNT_GREEKS];
+    val[EST_CALL] = s * eq * nd1 - k * er * nd2;
+    val[EST_PUT] = k * er * md2 - s * eq * md1;
+    val[EST_CALL_DELTA] = eq * nd1;
+    val[EST_PUT_DELTA] = -eq * md1;
+    val[EST_GAMMA] = eq * pdf / (s * vs);
+    val[EST_VEGA] = eq * pdf * s * sq / 100.0;
+    val[EST_CALL_RHO] = k * t * er * nd2 / 100.0;
+    val[EST_PUT_RHO] = -k * t * er * md2 / 100.0;
+    val[EST_CALL_THETA] = decay - r * k * er * nd2 + q * s * eq * nd1;
+    val[EST_PUT_THETA] = decay + r * k * er * md2 - q * s * eq * md1;
+#pragma unroll
+    for (int e = 0; e < EST_COUNT_GREEKS; ++e)
+        if (a.out[e]) a.out[e][o] = (float)val[e];
+}
+
 // ------------------------------------------------------------------------------------------------ RNG substreams
 // pool[i] = jump^(first + i)(base): thread i applies the precomputed polynomials x^(2^(128+k)) for the set bits of
 // (first + i).  Replaces per-chunk OS-entropy seeding (mc_simd.rs:52-54) with non-overlapping 2^128-long substreams.

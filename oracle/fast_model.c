@@ -55,6 +55,23 @@ static inline float fast_quad_increment(xo256_t *g, float acc) {
     return bm_term(low_bytes23(w0, w2, w4), low_bytes23(w1, w3, w5), acc);
 }
 
+/* The four Box-Muller terms of `n` consecutive quads, separately (out[4*i + j], j = 0..3 for pairs A, B, C, D):
+ * lets the tests check that pair D -- built from the low bytes pairs A-C leave over -- is a standard Box-Muller
+ * variate of the same law and uncorrelated with the others. */
+void fast_model_quad_terms(uint64_t state[4], int n, float *out) {
+    xo256_t g; memcpy(g.s, state, 32);
+    for (int i = 0; i < n; i++) {
+        const uint64_t x0 = xo256pp_next(&g), x1 = xo256pp_next(&g), x2 = xo256pp_next(&g);
+        const uint32_t w0 = (uint32_t)(x0 >> 32), w1 = (uint32_t)x0, w2 = (uint32_t)(x1 >> 32), w3 = (uint32_t)x1;
+        const uint32_t w4 = (uint32_t)(x2 >> 32), w5 = (uint32_t)x2;
+        out[4 * i + 0] = bm_term(top23(w0), top23(w1), 0.0f);
+        out[4 * i + 1] = bm_term(top23(w2), top23(w3), 0.0f);
+        out[4 * i + 2] = bm_term(top23(w4), top23(w5), 0.0f);
+        out[4 * i + 3] = bm_term(low_bytes23(w0, w2, w4), low_bytes23(w1, w3, w5), 0.0f);
+    }
+    memcpy(state, g.s, 32);
+}
+
 /* Run `n_paths` consecutive paths of `half_steps` pairs each from one stream.  state is advanced in place.
  * out_m[p] = accumulated sum M' of path p (units: sqrt(2 ln 2) smaller than the reference's M). */
 void fast_model_stream_paths(uint64_t state[4], int half_steps, int n_paths, float *out_m) {

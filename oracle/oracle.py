@@ -54,6 +54,8 @@ def lib():
         L.ref_splitmix64.argtypes = [_u64p]
         L.fast_model_stream_paths.restype = None
         L.fast_model_stream_paths.argtypes = [_u64p, C.c_int, C.c_int, _fp]
+        L.fast_model_quad_terms.restype = None
+        L.fast_model_quad_terms.argtypes = [_u64p, C.c_int, _fp]
         L.fast_model_constants.restype = None
         L.fast_model_constants.argtypes = [_f] * 5 + [_fp, _fp]
         L.fast_model_growth.restype = _f
@@ -136,6 +138,14 @@ def fast_stream_paths(state, half_steps, n_paths):
     st = np.array(state, dtype=np.uint64)
     out = np.empty(n_paths, np.float32)
     lib().fast_model_stream_paths(st.ctypes.data_as(_u64p), int(half_steps), int(n_paths), out.ctypes.data_as(_fp))
+    return out, st
+
+
+def fast_quad_terms(state, n):
+    """The four Box-Muller terms (pairs A, B, C, D) of n consecutive quads of the production convention: [n, 4]."""
+    st = np.array(state, dtype=np.uint64)
+    out = np.empty((n, 4), np.float32)
+    lib().fast_model_quad_terms(st.ctypes.data_as(_u64p), int(n), out.ctypes.data_as(_fp))
     return out, st
 
 

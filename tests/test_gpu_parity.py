@@ -397,3 +397,32 @@ def test_trials_sharded_over_substream_blocks(pkg, oracle):
         exact = oracle.bs64("call_price", s, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
         assert abs(out[0, i] - exact) <= 3.5 * out[2, i]
         assert out[2, i] < 0.08        # ~ sigma_payoff / sqrt(80000)
+
+
+def test_closed_form_batch_matches_golden(ctx, oracle, bs_cases):
+    """mcb200_bs_batch (the reference's analytic oracle src/bs.rs as a batched GPU op) against the golden closed-form
+    vectors of the reference's own tests and the fp64 oracle on the C4 grid."""
+    names = ("call_price", "put_price", "call_delta", "put_delta", "gamma", "vega", "call_rho", "put_rho", "call_theta",
+             "put_theta")
+    keys = ("call", "put", "call_delta", "put_delta", "gamma", "vega", "call_rho", "put_rho", "call_theta", "put_theta")
+    cols = np.array([c["params"] for c in bs_cases], np.float32).T
+    got = ctx.bs_batch(*cols)
+    for i, c in enumerate(bs_cases):
+        key = keys[names.index(c["bs_function"])]
+        assert got[key][i] == pytest.approx(c["bs_f64"], rel=2e-6, abs=2e-6), c["reference_test"]
+        assert got[key][i] == pytest.approx(c["bs_f32"], rel=1e-4, abs=2e-5), c["reference_test"]   # bs.rs's f32 erf
+    spots = (50.0 + 112.0 * np.arange(0, 4096, 37) / 4096.0).astype(np.float32)
+    got = ctx.bs_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+    for name, key in zip(names, keys):
+        want = np.array([oracle.bs64(name, float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+                         for s in spots])
+        assert np.allclose(got[key], want, rtol=3e-6, atol=1e-7), name
+    z = ctx.greeks_batch_with_z(spots[::8], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 100.0, 40000.0)
+    # raw z-scores blow up where the estimator is almost deterministic (deep in/out of the money: sample SE -> 0 while
+    # the O(h^2) bias of the central difference and fp32 rounding remain), so the check floors the SE like the C4 test
+    floors = {"call": 2e-3, "put": 2e-3, "call_delta": 2e-4, "put_delta": 2e-4, "vega": 2e-4, "call_rho": 2e-4, "put_rho": 2e-4}
+    for key, floor in floors.items():
+        zz = np.abs(z[key] - z[key + "_bs"]) / np.maximum(z[key + "_se"], floor)
+        assert zz.max() < 4.5 and np.sqrt((zz ** 2).mean()) < 1.6, key
+        ok = z[key + "_se"] > floor
+        assert np.allclose(z[key + "_z"][ok], ((z[key] - z[key + "_bs"]) / z[key + "_se"])[ok])

@@ -146,3 +146,29 @@ def test_cpu_baseline_agrees_with_closed_form(oracle):
         for s, p in zip(spots, out):
             exact = oracle.bs64(name, float(s), 110.0, 0.25, 0.05, 0.5, 0.02)
             assert abs(p - exact) < 0.35, (kind, s, p, exact)   # ~4 SE at 40000 trials (SE <= 0.09)
+
+
+def test_quad_convention_terms_are_iid_normal(oracle, xoshiro_kat):
+    """Production convention (three generator outputs -> four Box-Muller pairs): every term, including pair D that is
+    gathered from the left-over low bytes, has the law sqrt(-log2 u) sin(theta) ~ N(0, 1/(2 ln 2)), and the four terms
+    of a quad are uncorrelated in value and in square.  (The GPU reproduces this model path by path:
+    tests/test_gpu_parity.py::test_production_stream_per_path_parity.)"""
+    n = 400000
+    t, _ = oracle.fast_quad_terms([0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9, 0x94d049bb133111eb, 0x2545f4914f6cdd1d], n)
+    t = t.astype(np.float64)
+    var = 1.0 / (2.0 * math.log(2.0))
+    for j in range(4):
+        x = t[:, j]
+        assert abs(x.mean()) < 4.0 * math.sqrt(var / n), j
+        assert abs(x.var() / var - 1.0) < 4.0 * math.sqrt(2.0 / n), j
+        assert abs((x ** 4).mean() / var ** 2 - 3.0) < 4.0 * math.sqrt(96.0 / n), j          # normal kurtosis
+        assert abs((x ** 3).mean()) / var ** 1.5 < 4.0 * math.sqrt(15.0 / n), j              # no skew
+        assert 4.0 < np.abs(x).max() / math.sqrt(var) <= 5.66       # 23-bit u1: the tail ends at sqrt(2*23*ln 2) = 5.65 sigma
+    c = np.corrcoef(t.T)
+    c2 = np.corrcoef((t ** 2).T)
+    off = ~np.eye(4, dtype=bool)
+    assert np.abs(c[off]).max() < 4.5 / math.sqrt(n) and np.abs(c2[off]).max() < 4.5 / math.sqrt(n)
+    # serial independence: term D of quad i against term A of quad i+1 (they share no generator output)
+    assert abs(np.corrcoef(t[:-1, 3], t[1:, 0])[0, 1]) < 4.5 / math.sqrt(n)
+    # sum of a quad = what a path accumulates: variance 4 * var
+    assert abs(t.sum(axis=1).var() / (4 * var) - 1.0) < 4.0 * math.sqrt(2.0 / n)
