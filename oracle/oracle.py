@@ -54,6 +54,8 @@ def lib():
         L.ref_splitmix64.argtypes = [_u64p]
         L.fast_model_stream_paths.restype = None
         L.fast_model_stream_paths.argtypes = [_u64p, C.c_int, C.c_int, _fp]
+        L.mc_scalar_price.restype = _f
+        L.mc_scalar_price.argtypes = [_f] * 9 + [C.c_uint64, _dp, _dp]
         L.fast_model_quad_terms.restype = None
         L.fast_model_quad_terms.argtypes = [_u64p, C.c_int, _fp]
         L.fast_model_constants.restype = None
@@ -139,6 +141,15 @@ def fast_stream_paths(state, half_steps, n_paths):
     out = np.empty(n_paths, np.float32)
     lib().fast_model_stream_paths(st.ctypes.data_as(_u64p), int(half_steps), int(n_paths), out.ctypes.data_as(_fp))
     return out, st
+
+
+def mc_scalar(spot, strike, vol, r, years, q, steps, num_trials, call_mult=1.0, seed=1):
+    """The reference's scalar pricer src/mc.rs (one normal and one exp per step, multiplicative path), seedable:
+    dict(price=f32 as mc.rs returns it, mean=fp64 mean, se=fp64 standard error)."""
+    mean, se = C.c_double(), C.c_double()
+    price = lib().mc_scalar_price(spot, strike, vol, r, years, q, steps, num_trials, call_mult, int(seed),
+                                  C.byref(mean), C.byref(se))
+    return dict(price=float(price), mean=mean.value, se=se.value)
 
 
 def fast_quad_terms(state, n):

@@ -426,3 +426,16 @@ def test_closed_form_batch_matches_golden(ctx, oracle, bs_cases):
         assert zz.max() < 4.5 and np.sqrt((zz ** 2).mean()) < 1.6, key
         ok = z[key + "_se"] > floor
         assert np.allclose(z[key + "_z"][ok], ((z[key] - z[key + "_bs"]) / z[key + "_se"])[ok])
+
+
+def test_gpu_agrees_with_scalar_mc_algorithm(ctx, oracle):
+    """Independent-algorithm cross-check: the reference's scalar pricer src/mc.rs -- one normal and
+    one exp per step, multiplicative path, different normal generator -- against the GPU path, 3 combined SEs."""
+    spots = np.array([95.0, 110.0, 125.0], np.float32)
+    res = ctx.price_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 60.0, 200000.0)
+    for i, s in enumerate(spots):
+        for mult, key in ((1.0, "call"), (-1.0, "put")):
+            ref = oracle.mc_scalar(float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 60.0, 60000.0,
+                                   mult, seed=100 + i)
+            tol = 3.0 * math.hypot(float(res[key + "_se"][i]), ref["se"]) + 1e-3
+            assert abs(float(res[key][i]) - ref["mean"]) <= tol, (s, key, float(res[key][i]), ref)

@@ -172,3 +172,31 @@ def test_quad_convention_terms_are_iid_normal(oracle, xoshiro_kat):
     assert abs(np.corrcoef(t[:-1, 3], t[1:, 0])[0, 1]) < 4.5 / math.sqrt(n)
     # sum of a quad = what a path accumulates: variance 4 * var
     assert abs(t.sum(axis=1).var() / (4 * var) - 1.0) < 4.0 * math.sqrt(2.0 / n)
+
+
+def test_scalar_mc_replays_mc_rs_tests(oracle, bs_cases):
+    """src/mc.rs:75-121: the six tests of the scalar pricer, same parameters and tolerances, on its restatement."""
+    cases = [c for c in bs_cases if c["reference_test"].startswith("mc.rs")]
+    assert len(cases) == 6
+    for c in cases:
+        s, k, v, r, t, q = c["params"]
+        mult = 1.0 if c["mc_function"] == "call_price" else -1.0
+        got = oracle.mc_scalar(s, k, v, r, t, q, float(c["steps"]), float(c["trials"]), mult, seed=11)
+        assert abs(got["price"] - c["bs_f32"]) <= c["tolerance"], (c["reference_test"], got)
+        assert abs(got["mean"] - c["bs_f64"]) <= 4.0 * got["se"] + 1e-3, (c["reference_test"], got)
+
+
+def test_scalar_mc_and_simd_restatement_agree(oracle):
+    """Two independent algorithms (per-step exp + polar normals vs pair-summed Box-Muller in log space) price the same
+    option within 3 combined standard errors; with an odd step count only the scalar one keeps the full variance."""
+    s, k, v, r, t, q = 105.0, 110.0, 0.25, 0.05, 0.5, 0.02
+    a = oracle.mc_scalar(s, k, v, r, t, q, 50.0, 40000.0, 1.0, seed=3)
+    seeds = oracle.chunk_seeds(40000 // 8, 17)
+    b = oracle.pricing_detail(s, k, v, r, t, q, 50.0, 40000.0, 1.0, seeds)
+    assert abs(a["mean"] - b["mean"]) <= 3.0 * math.hypot(a["se"], b["se"])
+    exact = oracle.bs64("call_price", s, k, v, r, t, q)
+    assert abs(a["mean"] - exact) <= 3.5 * a["se"]
+    odd_scalar = oracle.mc_scalar(s, k, v, r, t, q, 5.0, 40000.0, 1.0, seed=5)
+    odd_simd = oracle.pricing_detail(s, k, v, r, t, q, 5.0, 40000.0, 1.0, seeds)
+    assert abs(odd_scalar["mean"] - exact) <= 3.5 * odd_scalar["se"]
+    assert odd_simd["mean"] < exact - 5.0 * odd_simd["se"]          # 4 of 5 normals: under-dispersed (mc_simd.rs:44,47)
