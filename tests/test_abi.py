@@ -118,6 +118,27 @@ def test_no_cpu_fallback(pkg):
     assert math.isnan(v) and "no CPU path" in pkg.mc_simd.last_error()
 
 
+def _build_c_client(pkg, tmp_path):
+    """gcc -std=c99 against include/mcb200.h, linked with libmcb200.so only."""
+    import subprocess
+    pkg.build()
+    exe = str(tmp_path / "c_abi_client")
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "c_client", "c_abi_client.c"), "-L", libdir, "-lmcb200", "-lm",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    return exe
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
+def test_plain_c_client_links_and_fails_loudly_without_gpu(pkg, tmp_path):
+    import subprocess
+    res = subprocess.run([_build_c_client(pkg, tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    assert "c client ok (no device)" in res.stdout
+
+
 def test_product_never_imports_the_oracle():
     pkg_dir = os.path.join(ROOT, "monte-carlo-options-simd_b200")
     for dirpath, _, files in os.walk(pkg_dir):

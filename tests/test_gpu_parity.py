@@ -425,7 +425,7 @@ def test_closed_form_batch_matches_golden(ctx, oracle, bs_cases):
         zz = np.abs(z[key] - z[key + "_bs"]) / np.maximum(z[key + "_se"], floor)
         assert zz.max() < 4.5 and np.sqrt((zz ** 2).mean()) < 1.6, key
         ok = z[key + "_se"] > floor
-        assert np.allclose(z[key + "_z"][ok], ((z[key] - z[key + "_bs"]) / z[key + "_se"])[ok])
+        assert np.allclose(z[key + "_z"][ok], (z[key][ok] - z[key + "_bs"][ok]) / z[key + "_se"][ok])
 
 
 def test_gpu_agrees_with_scalar_mc_algorithm(ctx, oracle):
@@ -454,3 +454,13 @@ def test_long_segments_flush_in_fp64(ctx, oracle):
         n = plan["n_paths"]
         assert abs(res[key][0] * trials / n - exact) <= 3.5 * res[key + "_se"][0] + 2e-6 * exact, (key, res[key][0], exact)
         assert 2e-4 < res[key + "_se"][0] < 8e-4
+
+
+def test_plain_c_client_on_gpu(pkg, tmp_path):
+    """The C99 client of include/mcb200.h (tests/c_client/c_abi_client.c) prices through the drop-in and the batched
+    entry point: the boundary needs nothing but the header and the shared library."""
+    import subprocess
+    from test_abi import _build_c_client
+    res = subprocess.run([_build_c_client(pkg, tmp_path), "gpu"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    assert "c client ok (gpu)" in res.stdout

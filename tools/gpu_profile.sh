@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for one workload (run under gpurun, one GPU): launch list + full capture of the fused path kernel.
 W=${1:-c2}
-CMD="python bench.py --workload $W --steps 3 --warmup 3 --roof-seconds 0 --no-cpu"
+CMD="python bench.py --workload $W --steps ${NCU_STEPS:-3} --warmup 3 --roof-seconds 0 --no-cpu"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$W.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_list_$W.log 2>&1
