@@ -198,6 +198,8 @@ int run_microbench(cudaStream_t st, int sm_count, mcb200_pipe_rate* out, int cap
     run_pair<0, 0, false, 4, 0>(b, 4); run_pair<0, 0, false, 4, 0>(b, 3); run_pair<0, 0, false, 4, 0>(b, 2);
     run_pair<0, 0, false, 8, 0>(b, 4); run_pair<0, 0, false, 8, 0>(b, 2);
     run_pair<0, 9, false, 2, 0>(b, 4); run_pair<0, 9, false, 1, 0>(b, 4); run_pair<0, 9, false, 2, 0>(b, 8);   // quad_fast
+    run_pair<0, 9, false, 4, 0>(b, 4); run_pair<0, 9, false, 2, 0>(b, 2); run_pair<0, 9, false, 2, 0>(b, 1, 256);
+    run_pair<0, 9, false, 4, 0>(b, 1, 256); run_pair<0, 9, false, 2, 0>(b, 1, 128); run_pair<0, 9, false, 4, 0>(b, 1, 128);
     // few warps per SM (named by resident warps per SM): how much of the pipe can 1 or 2 warps per sub-partition use?
     run_pair<0, 0, false, 8, 0>(b, 1, 256); run_pair<0, 0, false, 8, 0>(b, 1, 128); run_pair<0, 0, false, 4, 0>(b, 1, 128);
     run_pair<0, 0, false, 8, 0>(b, 1, 32);
