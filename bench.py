@@ -352,9 +352,10 @@ def b200_arm(args, w):
                          "unit": "path-steps/s", "frac": frac, "traffic": ncu_traffic(args.workload),
                          "traffic_note": "DRAM bytes per launch (ncu): the per-thread generator states, read once; "
                                          "path data never leaves registers",
-                         "alu_pipe_ceiling_frac": 3.33 * 2.0 / ROOFLINE_PATH_STEPS_PER_CLK_PER_SM,
-                         "alu_pipe_ceiling_note": "the inner step alone sustains 3.33 pairs/clk/SM on B200 (ALU pipe "
-                                                  "saturated, profiles/r1_microbench_v2_pipes.json): 83% of this peak",
+                         "inner_step_ceiling_frac": 3.95 * 2.0 / ROOFLINE_PATH_STEPS_PER_CLK_PER_SM,
+                         "inner_step_ceiling_note": "the inner step (quad_fast: 3 xoshiro256++ outputs -> 4 Box-Muller "
+                                                    "pairs) alone sustains 3.95 pairs/clk/SM on B200 with the ALU pipe "
+                                                    "88% busy (profiles/r1_microbench_v2_pipes.json): 99% of this peak",
                          "kernel": "simulate_kernel", "kernel_ms": sim_avg_ms, "launches_timed": len(sim_ms),
                          "peak_basis": "%d SMs x %.0f MHz (MEASURED_PEAKS.json sm_max_mhz%s) x 8 path-steps/clk/SM"
                                        % (info0["sm_count"], sm_max_mhz, "" if peaks else ", fallback"),
