@@ -239,8 +239,7 @@ struct Request {
     Bumps bumps{1.0f, 1.0f, 1.0f, 1.0f};
     const uint64_t* chunk_seeds = nullptr;   // device
     float* growth_out = nullptr;             // device
-    bool use_inline = false;                 // n == 1 host call: inputs travel in the launch parameters
-    float inline_opt[6] = {0, 0, 0, 0, 0, 0};
+    const float* const* inline_cols = nullptr;   // host columns of a small batch: they travel in the launch parameters
 };
 
 template <int STREAM, int PAYOFF, bool DUMP>
@@ -304,10 +303,9 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.moments_out = moments_out; a.finalize = finalize ? 1 : 0;
     a.fin = make_finalize(n_est, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out, out_se);
     a.growth_out = rq.growth_out;
-    if (rq.use_inline) {
-        a.use_inline = 1; a.fin.use_inline = 1;
-        for (int k = 0; k < 6; ++k) a.inline_opt[k] = rq.inline_opt[k];
-        a.fin.inline_rate = rq.inline_opt[3]; a.fin.inline_years = rq.inline_opt[4];
+    if (rq.inline_cols) {
+        a.use_inline = 1;
+        for (int k = 0; k < 6; ++k) std::memcpy(a.inline_opt[k], rq.inline_cols[k], sizeof(float) * rq.n);
     }
     const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
@@ -436,14 +434,13 @@ static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps,
     Request rq;
     rq.n = n; rq.steps = steps; rq.num_trials = num_trials; rq.payoff = payoff; rq.stream_mode = stream_mode;
     rq.bumps = bumps; rq.dump = dump;
-    // Small batches skip the copy engines: a single option carries its six inputs in the launch parameters, and up to
-    // kDirectWriteMaxOptions options have their results written by the kernel straight into the mapped pinned staging
-    // buffer (posted PCIe writes).  One launch + one stream synchronize is then the whole call.
-    const bool inline_in = (n == 1 && pl.n_paths > 0);
+    // Small batches skip the copy engines: up to kInlineMaxOptions options carry their six input columns in the launch
+    // parameters, and up to kDirectWriteMaxOptions options have their results written by the kernel straight into the
+    // mapped pinned staging buffer (posted PCIe writes).  One launch + one stream synchronize is then the whole call.
+    const bool inline_in = (n <= kInlineMaxOptions && pl.n_paths > 0);
     const bool direct_out = (n <= kDirectWriteMaxOptions);
     if (inline_in) {
-        rq.use_inline = true;
-        for (int k = 0; k < 6; ++k) rq.inline_opt[k] = in[k][0];
+        rq.inline_cols = in;
     } else {
         for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
         CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));

@@ -39,7 +39,6 @@ struct FinalizeSpec {       // how per-option moment sums become prices / Greeks
     double n_paths;          // paths simulated in total (all shards)
     double num_trials;       // divisor, as passed by the caller (mc_simd.rs:77 divides by num_trials)
     const float* rate; const float* years;
-    int use_inline; float inline_rate, inline_years;   // single-option calls carry their inputs in the launch parameters
     Bumps bumps;
     float* out[EST_COUNT_GREEKS];      // estimator values (nullable)
     float* out_se[EST_COUNT_GREEKS];   // their standard errors (nullable)
@@ -63,8 +62,10 @@ struct SimArgs {
     int finalize;            // non-zero: the last warp to finish an option also writes fin.out / fin.out_se
     FinalizeSpec fin;
     float* growth_out;       // DUMP only: [n_options][n_paths] terminal growth factors S_T / spot
-    int use_inline;          // n_options == 1 from a host call: the six inputs ride in the launch parameters (no H2D copy)
-    float inline_opt[6];     // spot, strike, vol, rate, years, div
+    // Small host batches (n_options <= kInlineMaxOptions) carry their six input columns in the launch parameters, so
+    // the call needs no H2D copy at all.
+    int use_inline;
+    float inline_opt[6][kInlineMaxOptions];     // spot, strike, vol, rate, years, div
 };
 
 // f32 constants exactly as the reference computes them (mc_simd.rs:36-45), then rescaled to base-2 exponent units.
@@ -91,8 +92,8 @@ template <int STREAM, int PAYOFF>
 __device__ __forceinline__ void load_option_constants(const SimArgs& a, int o, float* sc) {
     float spot, strike, vol, rate, years, div;
     if (a.use_inline) {
-        spot = a.inline_opt[0]; strike = a.inline_opt[1]; vol = a.inline_opt[2];
-        rate = a.inline_opt[3]; years = a.inline_opt[4]; div = a.inline_opt[5];
+        spot = a.inline_opt[0][o]; strike = a.inline_opt[1][o]; vol = a.inline_opt[2][o];
+        rate = a.inline_opt[3][o]; years = a.inline_opt[4][o]; div = a.inline_opt[5][o];
     } else {
         spot = a.opt.spot[o]; strike = a.opt.strike[o]; vol = a.opt.vol[o];
         rate = a.opt.rate[o]; years = a.opt.years[o]; div = a.opt.div[o];
@@ -165,9 +166,9 @@ __device__ __forceinline__ float evaluate_path(float m, const float* sc, float (
 
 // ------------------------------------------------------------------------------------------------ finalisation
 // mean = sum / num_trials * scale ; se = sample std of the per-path estimator / sqrt(n) * (n / num_trials) * scale
-__device__ __forceinline__ void finalize_estimator(const FinalizeSpec& f, int o, int e, double s, double ss) {
-    const float disc = f.use_inline ? expf(-f.inline_rate * f.inline_years)
-                                    : expf(-f.rate[o] * f.years[o]);                      // mc_simd.rs:77
+__device__ __forceinline__ void finalize_estimator(const FinalizeSpec& f, int o, int e, double s, double ss, float rate,
+                                                   float years) {
+    const float disc = expf(-rate * years);                       // mc_simd.rs:77
     double scale;
     switch (e) {
         case EST_CALL: case EST_PUT: scale = disc; break;
@@ -190,7 +191,7 @@ __global__ void finalize_kernel(const double* __restrict__ moments, int n_option
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_options * n_est) return;
     const int o = idx / n_est, e = idx - o * n_est;
-    finalize_estimator(f, o, e, moments[(size_t)idx * 2], moments[(size_t)idx * 2 + 1]);
+    finalize_estimator(f, o, e, moments[(size_t)idx * 2], moments[(size_t)idx * 2 + 1], f.rate[o], f.years[o]);
 }
 
 // Rounds [w*R/W, (w+1)*R/W) belong to warp w; the warp that owns round r is therefore ceil((r+1)*W/R) - 1.
@@ -210,7 +211,7 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 //     bit-reproducible, independent of which warp arrives last) and writes moments and/or final values and SEs.
 // Path data never leaves registers.
 template <int STREAM, int PAYOFF, bool DUMP>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const SimArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const __grid_constant__ SimArgs a) {
     constexpr int kEst = PayoffTraits<PAYOFF>::kEst;
     constexpr int kAcc = 2 * kEst;
     constexpr int kConst = PayoffTraits<PAYOFF>::kConst;
@@ -339,7 +340,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 if (a.finalize) {
                     const double sum = __shfl_sync(0xffffffffu, s, (2 * lane) & 31);
                     const double sq = __shfl_sync(0xffffffffu, s, (2 * lane + 1) & 31);
-                    if (lane < kEst) finalize_estimator(a.fin, o, lane, sum, sq);
+                    if (lane < kEst)
+                        finalize_estimator(a.fin, o, lane, sum, sq, a.use_inline ? a.inline_opt[3][o] : a.opt.rate[o],
+                                           a.use_inline ? a.inline_opt[4][o] : a.opt.years[o]);
                 }
                 if (lane == 0) a.arrivals[o] = 0u;           // leave the counter clean for the next launch
             }

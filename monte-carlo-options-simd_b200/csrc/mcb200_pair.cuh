@@ -14,6 +14,7 @@ constexpr int kWarps = kThreads / 32;
 // is bound by the ALU pipe, not by latency: measured 3.32 pairs/clk/SM at 8 CTAs/SM and 3.32 at 4 with unroll 8
 // (profiles/r1_microbench_v2_pipes.json), so half occupancy costs nothing and buys register-resident accumulators.
 constexpr int kMinCtasPerSm = 4;
+constexpr int kInlineMaxOptions = 128;      // host batches up to this size travel in the launch parameters (3 KB)
 constexpr int kMaxRoundsPerFlush = 4096;   // paths a thread sums in fp32 before its moments go to fp64
 
 // ------------------------------------------------------------------------------------------------ math helpers
