@@ -464,3 +464,32 @@ def test_plain_c_client_on_gpu(pkg, tmp_path):
     res = subprocess.run([_build_c_client(pkg, tmp_path), "gpu"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
     assert "c client ok (gpu)" in res.stdout
+
+
+def test_c5_sweep_z_scores_are_standard_normal(ctx):
+    """Config 5 grid (400 spots x 250 strikes = 1e5 pairs) at 1e4 trials x 252 steps: across the ~2.3e4 pairs that are
+    not far from the money, the z-scores (estimate - closed form) / SE must look like N(0,1).  With this many options
+    the mean z is resolved to +-0.007, so a bias of a few percent of one standard error -- a deficit of variance from
+    correlated substreams, a distorted normal tail, a wrong drift -- would show."""
+    sp = (50.0 + 112.0 * np.arange(400) / 400.0).astype(np.float32)
+    st = (80.0 + 60.0 * np.arange(250) / 250.0).astype(np.float32)
+    spots, strikes = np.repeat(sp, 250), np.tile(st, 400)
+    res = ctx.price_batch(spots, strikes, GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 252.0, 1e4)
+    bs = ctx.bs_batch(spots, strikes, GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+    near = (bs["call_delta"] > 0.25) & (bs["call_delta"] < 0.75)
+    assert near.sum() > 20000
+    for key in ("call", "put"):
+        z = (res[key][near].astype(np.float64) - bs[key][near]) / res[key + "_se"][near]
+        n = z.size
+        # the sample SE of a skewed payoff is correlated with the estimate: E[z] ~ -skew / (2 sqrt(trials)) ~ -0.01
+        assert abs(z.mean()) < 0.03, (key, z.mean())
+        assert 0.98 < z.std() < 1.03, (key, z.std())
+        assert (np.abs(z) > 3.0).mean() < 0.006 and np.abs(z).max() < 6.0, (key, np.abs(z).max())
+    # call - put = e^{-rT} (mean S_T - K): a martingale test of the simulated paths with an exactly known standard error,
+    # sd(S_T) = S0 e^{(r-q)T} sqrt(e^{v^2 T} - 1) -- for every one of the 1e5 pairs, far from the money included
+    disc_q, disc_r = math.exp(-GRID["q"] * GRID["t"]), math.exp(-GRID["r"] * GRID["t"])
+    parity = res["call"].astype(np.float64) - res["put"] - (spots * disc_q - strikes * disc_r)
+    se_par = spots * disc_q * math.sqrt(math.exp(GRID["vol"] ** 2 * GRID["t"]) - 1.0) / math.sqrt(1e4)
+    zp = parity / se_par
+    assert abs(zp.mean()) < 4.0 / math.sqrt(zp.size) and 0.985 < zp.std() < 1.015 and np.abs(zp).max() < 5.5, (
+        zp.mean(), zp.std(), np.abs(zp).max())

@@ -200,3 +200,26 @@ def test_scalar_mc_and_simd_restatement_agree(oracle):
     odd_simd = oracle.pricing_detail(s, k, v, r, t, q, 5.0, 40000.0, 1.0, seeds)
     assert abs(odd_scalar["mean"] - exact) <= 3.5 * odd_scalar["se"]
     assert odd_simd["mean"] < exact - 5.0 * odd_simd["se"]          # 4 of 5 normals: under-dispersed (mc_simd.rs:44,47)
+
+
+def test_jump_substreams_are_uncorrelated(oracle, xoshiro_kat):
+    """The reference only tests lane-0 moments (rand32x8.rs:68-81).  Neighbouring substreams of the production layout
+    -- thread t uses jump^t of the seed state, GPU g uses long_jump^g -- must be uncorrelated: cross-correlation of the
+    uniforms of streams t and t+1 (and of GPU blocks 0 and 1) at lags 0 and 1, plus per-stream moments."""
+    n = 200000
+    base = xoshiro_kat["state"]
+    jump, long_jump = xoshiro_kat["jump_poly"], xoshiro_kat["long_jump_poly"]
+    streams = [base, oracle.xoshiro_apply_poly(base, jump), oracle.xoshiro_apply_poly(base, long_jump)]
+    streams.append(oracle.xoshiro_apply_poly(streams[1], jump))
+    u = []
+    for st in streams:
+        out, _ = oracle.xoshiro_outputs(st, n)
+        u.append((np.asarray(out, np.uint64) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53)
+    for x in u:
+        assert abs(x.mean() - 0.5) < 4.0 / math.sqrt(12 * n) and abs(x.var() - 1 / 12) < 4.0 * math.sqrt(1 / 180 / n)
+    bound = 4.5 / math.sqrt(n)
+    for a in range(len(u)):
+        for b in range(a + 1, len(u)):
+            assert abs(np.corrcoef(u[a], u[b])[0, 1]) < bound, (a, b)
+            assert abs(np.corrcoef(u[a][1:], u[b][:-1])[0, 1]) < bound, (a, b)
+            assert abs(np.corrcoef(u[a][:-1], u[b][1:])[0, 1]) < bound, (a, b)
