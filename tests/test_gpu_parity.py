@@ -493,3 +493,35 @@ def test_c5_sweep_z_scores_are_standard_normal(ctx):
     zp = parity / se_par
     assert abs(zp.mean()) < 4.0 / math.sqrt(zp.size) and 0.985 < zp.std() < 1.015 and np.abs(zp).max() < 5.5, (
         zp.mean(), zp.std(), np.abs(zp).max())
+
+
+def test_dropins_are_callable_from_many_threads(pkg):
+    """The reference's functions are re-entrant (callers may sit on a rayon pool); the drop-ins share one context
+    behind a mutex and must stay correct under concurrent blocking calls."""
+    import threading
+    pkg.mc_simd.reset_default_context(device=0, seed=77)
+    results, errors = [], []
+
+    def worker(k):
+        try:
+            for i in range(25):
+                c = pkg.mc_simd.call_price(100.0 + k, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 20000.0)
+                p = pkg.mc_simd.put_price_av(100.0 + k, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 20000.0)
+                d = pkg.mc_simd.call_delta(100.0 + k, 0.01, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 20000.0)
+                results.append((k, c, p, d))
+        except Exception as e:                      # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and len(results) == 150
+    from oracle import oracle
+    for k, c, p, d in results:
+        s = 100.0 + k
+        assert abs(c - oracle.bs64("call_price", s, 110.0, 0.25, 0.05, 0.5, 0.02)) < 0.6        # ~4.5 SE at 2e4 trials
+        assert abs(p - oracle.bs64("put_price", s, 110.0, 0.25, 0.05, 0.5, 0.02)) < 0.6
+        assert abs(d - oracle.bs64("call_delta", s, 110.0, 0.25, 0.05, 0.5, 0.02)) < 0.03
+    assert len({c for _, c, _, _ in results}) == 150        # every call drew fresh paths
