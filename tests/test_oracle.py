@@ -223,3 +223,19 @@ def test_jump_substreams_are_uncorrelated(oracle, xoshiro_kat):
             assert abs(np.corrcoef(u[a], u[b])[0, 1]) < bound, (a, b)
             assert abs(np.corrcoef(u[a][1:], u[b][:-1])[0, 1]) < bound, (a, b)
             assert abs(np.corrcoef(u[a][:-1], u[b][1:])[0, 1]) < bound, (a, b)
+
+
+@pytest.mark.parametrize("steps,trials,mult", [(100.0, 1000.0, 1.0), (37.0, 1007.0, -1.0), (252.0, 256.0, 1.0)])
+def test_two_independent_restatements_agree_per_path(oracle, steps, trials, mult):
+    """oracle/ref_mc.c (C, scalar loops) against oracle/np_restatement.py (numpy, written separately from
+    mc_simd.rs:9-79 and rand32x8.rs:5-21): same chunk seeds -> the same uniforms bit for bit, terminal sums and growth
+    factors equal to float32 libm-vs-numpy rounding, the same price."""
+    from oracle import np_restatement as npr
+    s, k, v, r, t, q = 103.0, 110.0, 0.25, 0.05, 0.5, 0.02
+    seeds = oracle.chunk_seeds(oracle.n_chunks(trials), 2718)
+    c = oracle.pricing_detail(s, k, v, r, t, q, steps, trials, mult, seeds, want_paths=True)
+    price, m, growth = npr.pricing(s, k, v, r, t, q, steps, trials, mult, seeds)
+    assert m.shape == c["m"].shape == (8 * (int(trials) // 8),)
+    assert np.max(np.abs(m - c["m"])) <= 2e-5 * max(1.0, float(np.abs(c["m"]).max()))
+    assert np.max(np.abs(growth - c["growth"]) / c["growth"]) < 5e-6
+    assert float(price) == pytest.approx(c["price"], rel=5e-6, abs=1e-6)
