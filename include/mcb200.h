@@ -119,6 +119,17 @@ int mcb200_price_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free_
                                  const double *moments, double total_paths, double total_num_trials,
                                  float *call_out, float *put_out, float *call_se, float *put_se, void *cuda_stream);
 
+/* The same three steps for the ten Greek estimators: moments[n][20] fp64 = {sum, sum^2} per estimator in the order of
+ * mcb200_greeks_batch (the per-path central differences are what is summed, so the moments add across GPUs). */
+int mcb200_greeks_moments_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
+                                 const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
+                                 const float *dividend_yield, float steps, float num_trials_local,
+                                 const mcb200_bumps *bumps, double *moments, void *cuda_stream);
+int mcb200_greeks_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free_rate, const float *years_to_expiry,
+                                  const double *moments, double total_paths, double total_num_trials,
+                                  const mcb200_bumps *bumps, float *const out[MCB200_N_GREEK_OUTPUTS],
+                                  float *const out_se[MCB200_N_GREEK_OUTPUTS], void *cuda_stream);
+
 /* ------------------------------------------------------------------ closed form (analytic companion) ----------- */
 /* Black-Scholes closed form with dividend yield for a batch -- the analytic value the reference's tests compare every
  * Monte Carlo estimate with (src/bs.rs:42-184, pub(crate) there).  Same units as bs.rs and as the estimators above:

@@ -93,6 +93,11 @@ def lib():
     L.mcb200_price_moments_device.argtypes = [_vp, C.c_int] + [_vp] * 6 + [_f, _f, C.c_uint, _vp, _vp]
     L.mcb200_price_finalize_device.restype = C.c_int
     L.mcb200_price_finalize_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double] + [_vp] * 4 + [_vp]
+    L.mcb200_greeks_moments_device.restype = C.c_int
+    L.mcb200_greeks_moments_device.argtypes = [_vp, C.c_int] + [_vp] * 6 + [_f, _f, C.POINTER(Bumps), _vp, _vp]
+    L.mcb200_greeks_finalize_device.restype = C.c_int
+    L.mcb200_greeks_finalize_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.POINTER(Bumps),
+                                                _VoidOut, _VoidOut, _vp]
     L.mcb200_bs_batch.restype = C.c_int
     L.mcb200_bs_batch.argtypes = [_vp, C.c_int] + six + [_GreekOut]
     L.mcb200_bs_batch_device.restype = C.c_int

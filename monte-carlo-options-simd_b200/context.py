@@ -216,6 +216,21 @@ class Context:
                                                      C.c_void_p(stream)))
 
 
+    def greeks_moments_device(self, n, in_ptrs, steps, num_trials_local, bumps, moments_ptr, stream=0):
+        b = N.Bumps(*bumps)
+        N.check(N.lib().mcb200_greeks_moments_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps,
+                                                     num_trials_local, C.byref(b), C.c_void_p(moments_ptr),
+                                                     C.c_void_p(stream)))
+
+    def greeks_finalize_device(self, n, rate_ptr, years_ptr, moments_ptr, total_paths, total_num_trials, bumps,
+                               out_ptrs, se_ptrs, stream=0):
+        b = N.Bumps(*bumps)
+        N.check(N.lib().mcb200_greeks_finalize_device(self._h, n, C.c_void_p(rate_ptr), C.c_void_p(years_ptr),
+                                                      C.c_void_p(moments_ptr), float(total_paths),
+                                                      float(total_num_trials), C.byref(b), N._VoidOut(*out_ptrs),
+                                                      N._VoidOut(*se_ptrs), C.c_void_p(stream)))
+
+
 class PreparedCall:
     """A C-ABI call with its host buffers bound (the ctypes marshalling is done once, not per call)."""
 

@@ -413,6 +413,38 @@ extern "C" int mcb200_price_finalize_device(mcb200_ctx* c, int n, const float* r
                         Bumps{1, 1, 1, 1}, out, se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
 }
 
+extern "C" int mcb200_greeks_moments_device(mcb200_ctx* c, int n, const float* spot, const float* strike,
+                                            const float* vol, const float* rate, const float* years, const float* div,
+                                            float steps, float num_trials_local, const mcb200_bumps* bumps,
+                                            double* moments, void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
+    if (n > 0 && !moments) return fail(MCB200_ERR_INVALID, "null moments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps;
+    rq.num_trials = num_trials_local; rq.payoff = PAYOFF_GREEKS; rq.bumps = to_bumps(bumps);
+    return run_sim(c, rq, moments, false, nullptr, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
+}
+
+extern "C" int mcb200_greeks_finalize_device(mcb200_ctx* c, int n, const float* rate, const float* years,
+                                             const double* moments, double total_paths, double total_num_trials,
+                                             const mcb200_bumps* bumps, float* const out[MCB200_N_GREEK_OUTPUTS],
+                                             float* const out_se[MCB200_N_GREEK_OUTPUTS], void* cuda_stream) {
+    const float* in[2] = {rate, years};
+    int rc = check_common(c, n, in, 2);
+    if (rc) return rc;
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
+    if (n > 0 && !moments) return fail(MCB200_ERR_INVALID, "null moments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return run_finalize(c, n, EST_COUNT_GREEKS, moments, total_paths, total_num_trials, rate, years, to_bumps(bumps), out,
+                        out_se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
 // ------------------------------------------------------------------------------------------------ host-buffer entry points
 constexpr int kDirectWriteMaxOptions = 4096;
 // Staging layout (floats): [6][n] inputs | [2*n_est][n] outputs (value rows then SE rows).

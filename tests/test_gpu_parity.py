@@ -525,3 +525,49 @@ def test_dropins_are_callable_from_many_threads(pkg):
         assert abs(p - oracle.bs64("put_price", s, 110.0, 0.25, 0.05, 0.5, 0.02)) < 0.6
         assert abs(d - oracle.bs64("call_delta", s, 110.0, 0.25, 0.05, 0.5, 0.02)) < 0.03
     assert len({c for _, c, _, _ in results}) == 150        # every call drew fresh paths
+
+
+def test_greeks_moment_path_equals_fused_path(pkg):
+    """mcb200_greeks_batch_device == mcb200_greeks_moments_device + mcb200_greeks_finalize_device bit for bit (the
+    trials-sharded route for the Greeks), and two half-sized shards on different substream blocks combine to an
+    estimate with the full-sample standard error."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    spots = torch.tensor([95.0, 105.0, 110.0, 118.0], dtype=torch.float32, device=dev)
+    n = spots.numel()
+    cols = [spots] + [torch.full((n,), v, dtype=torch.float32, device=dev) for v in
+                      (GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])]
+    ptrs = [c.data_ptr() for c in cols]
+    bumps = (0.01, 0.01, 0.01, 0.001)
+    a_out, a_se = torch.zeros(10, n, device=dev), torch.zeros(10, n, device=dev)
+    b_out, b_se = torch.zeros(10, n, device=dev), torch.zeros(10, n, device=dev)
+    mom = torch.zeros(n, 20, dtype=torch.float64, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    st = ts.cuda_stream
+    with pkg.Context(device=0, seed=8) as c:
+        c.greeks_batch_device(n, ptrs, 100.0, 40000.0, bumps, [a_out[i].data_ptr() for i in range(10)],
+                              [a_se[i].data_ptr() for i in range(10)], stream=st)
+        torch.cuda.synchronize()
+        c.set_seed(8)
+        c.greeks_moments_device(n, ptrs, 100.0, 40000.0, bumps, mom.data_ptr(), stream=st)
+        c.greeks_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), mom.data_ptr(), 40000.0, 40000.0, bumps,
+                                 [b_out[i].data_ptr() for i in range(10)], [b_se[i].data_ptr() for i in range(10)], stream=st)
+        torch.cuda.synchronize()
+    assert torch.equal(a_out, b_out) and torch.equal(a_se, b_se)
+    total = torch.zeros(n, 20, dtype=torch.float64, device=dev)
+    for rank in range(2):
+        m = torch.zeros(n, 20, dtype=torch.float64, device=dev)
+        with pkg.Context(device=0, seed=8, substream_block=rank) as c:
+            c.greeks_moments_device(n, ptrs, 100.0, 20000.0, bumps, m.data_ptr(), stream=st)
+            torch.cuda.synchronize()
+        total += m
+    with pkg.Context(device=0, seed=8) as c:
+        c.greeks_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), total.data_ptr(), 40000.0, 40000.0, bumps,
+                                 [b_out[i].data_ptr() for i in range(10)], [b_se[i].data_ptr() for i in range(10)], stream=st)
+        torch.cuda.synchronize()
+    # same sample size -> same standard errors to within their own sampling noise, estimates within 3 combined SEs
+    ratio = (b_se / a_se).cpu().numpy()
+    assert np.all((ratio > 0.8) & (ratio < 1.25))
+    z = ((b_out - a_out) / torch.hypot(a_se, b_se)).cpu().numpy()
+    assert np.abs(z).max() < 4.0
