@@ -27,7 +27,7 @@ typedef struct mcb200_ctx mcb200_ctx;
 
 typedef enum {
     MCB200_OK = 0,
-    MCB200_ERR_INVALID = 1,     /* bad argument (null pointer, n < 0, steps < 2, num_trials < 8, ...) */
+    MCB200_ERR_INVALID = 1,     /* bad argument: null pointer, n < 0, steps < 1, num_trials < 0, non-finite or > 2e9 */
     MCB200_ERR_CUDA = 2,        /* a CUDA runtime call failed; see mcb200_last_error() */
     MCB200_ERR_NO_DEVICE = 3,   /* no usable CUDA device (the library has no CPU path) */
     MCB200_ERR_NOMEM = 4
@@ -78,8 +78,11 @@ int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slo
 int mcb200_plan_warp_range(const mcb200_plan *plan, int warp, int64_t *first_round, int64_t *end_round);
 
 /* ------------------------------------------------------------------ batched entry points (new) ----------------- */
-/* Host buffers: inputs are copied to the device, outputs copied back, the call returns when they are valid.
- * Every option gets its own fresh paths (no sharing across options).  Output pointers may be NULL. */
+/* Host buffers: the call returns when the outputs are valid.  Inputs reach the device through a pinned staging copy
+ * (batches of <= 128 options ride in the launch parameters instead); outputs come back through a D2H copy (batches of
+ * <= 4096 options are written by the kernel straight into mapped pinned memory).  One kernel launch per call.
+ * Every option gets its own fresh paths (no sharing across options).  Output pointers may be NULL.
+ * num_trials < 8 simulates nothing and returns zeros, like the reference's empty chunk range (mc_simd.rs:49). */
 int mcb200_price_batch(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
                        const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
                        float steps, float num_trials, unsigned flags,
