@@ -133,6 +133,25 @@ int mcb200_greeks_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free
                                   const mcb200_bumps *bumps, float *const out[MCB200_N_GREEK_OUTPUTS],
                                   float *const out_se[MCB200_N_GREEK_OUTPUTS], void *cuda_stream);
 
+/* Fused variant of the trials-sharded operation: NO collective and no second kernel.  One GPU (the owner) holds an
+ * exchange buffer that the other processes map through CUDA IPC (peer memory over NVLink / NVSwitch).  Each rank's
+ * path kernel stores its finished per-option moment sums into its own row there and bumps a cross-GPU arrival counter;
+ * the warp that completes an option's count -- on whichever GPU -- sums the rows in rank order (deterministic) and
+ * writes price and standard error of the WHOLE sample into the buffer.
+ *   owner : mcb200_xgpu_create(ctx, n_max, world, 0, handle)      -> ship the 64 handle bytes to the other ranks
+ *   others: mcb200_xgpu_open(ctx, handle, n_max, world, 0)
+ *   all   : mcb200_price_xgpu_device(..., num_trials_local, flags, rank, total_paths, total_num_trials, stream)
+ *   all   : synchronize the stream, barrier across ranks, then mcb200_xgpu_results(ctx, n, call, put, call_se, put_se) */
+#define MCB200_IPC_HANDLE_BYTES 64
+int mcb200_xgpu_create(mcb200_ctx *ctx, int n_max, int world, int greeks, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES]);
+int mcb200_xgpu_open(mcb200_ctx *ctx, const uint8_t handle[MCB200_IPC_HANDLE_BYTES], int n_max, int world, int greeks);
+int mcb200_xgpu_close(mcb200_ctx *ctx);
+int mcb200_price_xgpu_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                             const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                             float steps, float num_trials_local, unsigned flags, int rank, double total_paths,
+                             double total_num_trials, void *cuda_stream);
+int mcb200_xgpu_results(mcb200_ctx *ctx, int n, float *call_out, float *put_out, float *call_se, float *put_se);
+
 /* ------------------------------------------------------------------ closed form (analytic companion) ----------- */
 /* Black-Scholes closed form with dividend yield for a batch -- the analytic value the reference's tests compare every
  * Monte Carlo estimate with (src/bs.rs:42-184, pub(crate) there).  Same units as bs.rs and as the estimators above:

@@ -15,6 +15,7 @@ N_GREEK_OUTPUTS = 10
 GREEK_NAMES = ("call", "put", "call_delta", "put_delta", "gamma", "vega", "call_rho", "put_rho", "call_theta",
                "put_theta")
 ANTITHETIC = 1
+IPC_HANDLE_BYTES = 64
 
 _f, _fp, _dp, _vp = C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p
 
@@ -98,6 +99,17 @@ def lib():
     L.mcb200_greeks_finalize_device.restype = C.c_int
     L.mcb200_greeks_finalize_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.POINTER(Bumps),
                                                 _VoidOut, _VoidOut, _vp]
+    L.mcb200_xgpu_create.restype = C.c_int
+    L.mcb200_xgpu_create.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.mcb200_xgpu_open.restype = C.c_int
+    L.mcb200_xgpu_open.argtypes = [_vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int]
+    L.mcb200_xgpu_close.restype = C.c_int
+    L.mcb200_xgpu_close.argtypes = [_vp]
+    L.mcb200_price_xgpu_device.restype = C.c_int
+    L.mcb200_price_xgpu_device.argtypes = ([_vp, C.c_int] + [_vp] * 6 + [_f, _f, C.c_uint, C.c_int, C.c_double,
+                                                                           C.c_double, _vp])
+    L.mcb200_xgpu_results.restype = C.c_int
+    L.mcb200_xgpu_results.argtypes = [_vp, C.c_int] + [_fp] * 4
     L.mcb200_bs_batch.restype = C.c_int
     L.mcb200_bs_batch.argtypes = [_vp, C.c_int] + six + [_GreekOut]
     L.mcb200_bs_batch_device.restype = C.c_int

@@ -231,6 +231,32 @@ class Context:
                                                       N._VoidOut(*se_ptrs), C.c_void_p(stream)))
 
 
+    # ------------------------------------------------------------------ cross-GPU fused combine (no collective)
+    def xgpu_create(self, n_max, world, greeks=False):
+        """Owner rank: allocate the exchange buffer; returns the 64 CUDA-IPC handle bytes to ship to the other ranks."""
+        h = (C.c_uint8 * N.IPC_HANDLE_BYTES)()
+        N.check(N.lib().mcb200_xgpu_create(self._h, int(n_max), int(world), 1 if greeks else 0, h))
+        return bytes(h)
+
+    def xgpu_open(self, handle, n_max, world, greeks=False):
+        h = (C.c_uint8 * N.IPC_HANDLE_BYTES).from_buffer_copy(bytes(handle))
+        N.check(N.lib().mcb200_xgpu_open(self._h, h, int(n_max), int(world), 1 if greeks else 0))
+
+    def xgpu_close(self):
+        N.check(N.lib().mcb200_xgpu_close(self._h))
+
+    def price_xgpu_device(self, n, in_ptrs, steps, num_trials_local, rank, total_paths, total_num_trials,
+                          antithetic=False, stream=0):
+        N.check(N.lib().mcb200_price_xgpu_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps, num_trials_local,
+                                                 N.ANTITHETIC if antithetic else 0, int(rank), float(total_paths),
+                                                 float(total_num_trials), C.c_void_p(stream)))
+
+    def xgpu_results(self, n):
+        out = [np.empty(n, np.float32) for _ in range(4)]
+        N.check(N.lib().mcb200_xgpu_results(self._h, n, *[N.fptr(o) for o in out]))
+        return dict(call=out[0], put=out[1], call_se=out[2], put_se=out[3])
+
+
 class PreparedCall:
     """A C-ABI call with its host buffers bound (the ctypes marshalling is done once, not per call)."""
 

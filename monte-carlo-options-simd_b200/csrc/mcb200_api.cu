@@ -85,6 +85,8 @@ struct mcb200_ctx {
     double* moments = nullptr; size_t moments_cap = 0;        // doubles (only for the zero-path corner)
     float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned+mapped host / device)
     float* h_stage_dev = nullptr;  // device-side address of h_stage: small batches write their results straight to it
+    // cross-GPU exchange buffer (trials-sharded fused combine): owned (cudaMalloc) or opened through CUDA IPC
+    void* xg_base = nullptr; bool xg_owner = false; int xg_world = 0, xg_n_max = 0, xg_n_acc = 0;
     uint64_t launches = 0;
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -206,6 +208,7 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (c->moments) cudaFree(c->moments);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
+    if (c->xg_base) { if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base); }
     delete c;
 }
 
@@ -240,7 +243,22 @@ struct Request {
     const uint64_t* chunk_seeds = nullptr;   // device
     float* growth_out = nullptr;             // device
     const float* const* inline_cols = nullptr;   // host columns of a small batch: they travel in the launch parameters
+    bool xg = false; int xg_rank = 0;            // cross-GPU fused combine through the context's exchange buffer
+    double xg_total_paths = 0, xg_total_trials = 0;
 };
+
+// Exchange buffer layout on the owner GPU: [world][n_max][n_acc] fp64 rows | [2 * n_est][n_max] f32 results | [n_max] u32
+struct XgLayout { double* slots; float* results; unsigned* arrivals; size_t bytes; };
+static XgLayout xg_layout_for(void* base, int world, int n_max, int n_acc) {
+    XgLayout L;
+    char* p = (char*)base;
+    L.slots = (double*)p; p += sizeof(double) * (size_t)world * n_max * n_acc;
+    L.results = (float*)p; p += sizeof(float) * (size_t)n_acc * n_max;
+    L.arrivals = (unsigned*)p; p += sizeof(unsigned) * (size_t)n_max;
+    L.bytes = (size_t)(p - (char*)base);
+    return L;
+}
+static XgLayout xg_layout(mcb200_ctx* c) { return xg_layout_for(c->xg_base, c->xg_world, c->xg_n_max, c->xg_n_acc); }
 
 template <int STREAM, int PAYOFF, bool DUMP>
 static void launch_sim(const SimArgs& a, int grid, cudaStream_t st) {
@@ -303,6 +321,12 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.moments_out = moments_out; a.finalize = finalize ? 1 : 0;
     a.fin = make_finalize(n_est, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out, out_se);
     a.growth_out = rq.growth_out;
+    if (rq.xg) {
+        XgLayout L = xg_layout(c);
+        a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_rank = rq.xg_rank; a.xg_world = c->xg_world;
+        a.xg_n_max = c->xg_n_max;
+        a.fin.n_paths = rq.xg_total_paths; a.fin.num_trials = rq.xg_total_trials;
+    }
     if (rq.inline_cols) {
         a.use_inline = 1;
         for (int k = 0; k < 6; ++k) std::memcpy(a.inline_opt[k], rq.inline_cols[k], sizeof(float) * rq.n);
@@ -443,6 +467,94 @@ extern "C" int mcb200_greeks_finalize_device(mcb200_ctx* c, int n, const float* 
     CU(cudaSetDevice(c->device));
     return run_finalize(c, n, EST_COUNT_GREEKS, moments, total_paths, total_num_trials, rate, years, to_bumps(bumps), out,
                         out_se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+// ------------------------------------------------------------------------------------------------ cross-GPU fused combine
+static_assert(sizeof(cudaIpcMemHandle_t) == MCB200_IPC_HANDLE_BYTES, "IPC handle size");
+
+static int xg_release(mcb200_ctx* c) {
+    if (c->xg_base) {
+        cudaStreamSynchronize(c->stream);
+        if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base);
+    }
+    c->xg_base = nullptr; c->xg_owner = false; c->xg_world = c->xg_n_max = c->xg_n_acc = 0;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_xgpu_create(mcb200_ctx* c, int n_max, int world, int greeks, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES]) {
+    if (!c || !handle_out || n_max <= 0 || world <= 0) return fail(MCB200_ERR_INVALID, "bad xgpu_create arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    xg_release(c);
+    const int n_acc = 2 * (greeks ? EST_COUNT_GREEKS : EST_COUNT_PRICE);
+    const XgLayout L = xg_layout_for(nullptr, world, n_max, n_acc);
+    CU(cudaMalloc(&c->xg_base, L.bytes));
+    CU(cudaMemset(c->xg_base, 0, L.bytes));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->xg_base));
+    std::memcpy(handle_out, &h, sizeof(h));
+    c->xg_owner = true; c->xg_world = world; c->xg_n_max = n_max; c->xg_n_acc = n_acc;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_xgpu_open(mcb200_ctx* c, const uint8_t handle[MCB200_IPC_HANDLE_BYTES], int n_max, int world, int greeks) {
+    if (!c || !handle || n_max <= 0 || world <= 0) return fail(MCB200_ERR_INVALID, "bad xgpu_open arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    xg_release(c);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(&c->xg_base, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xg_owner = false; c->xg_world = world; c->xg_n_max = n_max; c->xg_n_acc = 2 * (greeks ? EST_COUNT_GREEKS : EST_COUNT_PRICE);
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_xgpu_close(mcb200_ctx* c) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return xg_release(c);
+}
+
+// One launch per GPU, no collective: this GPU simulates num_trials_local trials of every option; the results of the
+// WHOLE sample (all ranks) appear in the exchange buffer once every rank's launch has finished.
+extern "C" int mcb200_price_xgpu_device(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                                        const float* rate, const float* years, const float* div, float steps,
+                                        float num_trials_local, unsigned flags, int rank, double total_paths,
+                                        double total_num_trials, void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (!c->xg_base) return fail(MCB200_ERR_INVALID, "no exchange buffer: call mcb200_xgpu_create / mcb200_xgpu_open first");
+    if (n > c->xg_n_max || rank < 0 || rank >= c->xg_world || c->xg_n_acc != 2 * EST_COUNT_PRICE)
+        return fail(MCB200_ERR_INVALID, "xgpu: n=%d (max %d), rank=%d (world %d)", n, c->xg_n_max, rank, c->xg_world);
+    mcb200_plan pl;
+    if (make_plan(n, steps, num_trials_local, c->grid_slots, &pl) != MCB200_OK || pl.n_paths == 0)
+        return fail(MCB200_ERR_INVALID, "xgpu: every rank must simulate at least 8 trials (steps=%g trials=%g)", steps, num_trials_local);
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials_local;
+    rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
+    rq.xg = true; rq.xg_rank = rank; rq.xg_total_paths = total_paths; rq.xg_total_trials = total_num_trials;
+    const XgLayout L = xg_layout(c);
+    float* out[2] = {L.results, L.results + c->xg_n_max};
+    float* se[2] = {L.results + 2 * (size_t)c->xg_n_max, L.results + 3 * (size_t)c->xg_n_max};
+    return run_sim(c, rq, nullptr, true, out, se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
+}
+
+// Copy the combined results out of the exchange buffer (peer read on non-owner ranks).  The caller must have
+// synchronised ALL ranks' launches first (stream synchronize + a barrier).
+extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float* put_out, float* call_se, float* put_se) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (!c->xg_base || n < 0 || n > c->xg_n_max) return fail(MCB200_ERR_INVALID, "xgpu_results: no exchange buffer or bad n");
+    const XgLayout L = xg_layout(c);
+    float* dst[4] = {call_out, put_out, call_se, put_se};
+    for (int k = 0; k < 4; ++k)
+        if (dst[k] && n > 0) CU(cudaMemcpy(dst[k], L.results + (size_t)k * c->xg_n_max, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return MCB200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer entry points

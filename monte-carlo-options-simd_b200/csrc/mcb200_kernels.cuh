@@ -65,6 +65,13 @@ struct SimArgs {
     // Small host batches (n_options <= kInlineMaxOptions) carry their six input columns in the launch parameters, so
     // the call needs no H2D copy at all.
     int use_inline;
+    // Cross-GPU fused combine (trials-sharded operation without a collective): every GPU stores the finished moment
+    // sums of an option into ITS row of an exchange buffer that lives on one GPU (peer memory over NVLink, mapped
+    // through CUDA IPC) and bumps the option's cross-GPU arrival counter; the warp -- on whichever GPU -- that completes
+    // the count sums the rows in rank order and finalises into the exchange buffer.  Null xg_slots = single-GPU launch.
+    double* xg_slots;        // [xg_world][xg_n_max][2 * kEst] on the owner GPU
+    unsigned* xg_arrivals;   // [xg_n_max] on the owner GPU, zero between launches
+    int xg_rank, xg_world, xg_n_max;
     float inline_opt[6][kInlineMaxOptions];     // spot, strike, vol, rate, years, div
 };
 
@@ -337,7 +344,29 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
 #pragma unroll
                 for (int off = kAccPad; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
                 if (a.moments_out && lane < kAcc) a.moments_out[(size_t)o * kAcc + lane] = s;
-                if (a.finalize) {
+                bool finish = a.finalize != 0;
+                if (a.xg_slots) {
+                    // this GPU's share of option o is complete: publish it to the owner GPU, count the arrival there
+                    volatile double* row = a.xg_slots + ((size_t)a.xg_rank * a.xg_n_max + (size_t)o) * kAcc;
+                    if (lane < kAcc) row[lane] = s;
+                    __threadfence_system();
+                    __syncwarp();
+                    unsigned seen = 0;
+                    if (lane == 0) seen = atomicAdd_system(a.xg_arrivals + o, 1u);
+                    seen = __shfl_sync(0xffffffffu, seen, 0);
+                    finish = finish && (int)seen == a.xg_world - 1;
+                    if (finish) {
+                        __threadfence_system();
+                        s = 0.0;
+                        if (lane < kAcc)
+                            for (int rk = 0; rk < a.xg_world; ++rk) {       // rank order: deterministic
+                                const volatile double* src = a.xg_slots + ((size_t)rk * a.xg_n_max + (size_t)o) * kAcc;
+                                s += src[lane];
+                            }
+                        if (lane == 0) *(volatile unsigned*)(a.xg_arrivals + o) = 0u;
+                    }
+                }
+                if (finish) {
                     const double sum = __shfl_sync(0xffffffffu, s, (2 * lane) & 31);
                     const double sq = __shfl_sync(0xffffffffu, s, (2 * lane + 1) & 31);
                     if (lane < kEst)

@@ -61,6 +61,30 @@ def main():
     out["trials_minor"] = dict(call=vals[0].tolist(), put=vals[1].tolist(), call_se=vals[2].tolist(),
                                put_se=vals[3].tolist(), spots=tspots.tolist(), total_paths=total_paths,
                                same_on_all_ranks=all(bool(torch.equal(g, vals)) for g in gathered))
+    # ---- trials-minor, FUSED: no collective and no second kernel -- every rank's path kernel stores its moment sums
+    #      into rank 0's exchange buffer (CUDA IPC peer memory over NVLink) and the last arrival finalises there
+    with pkg.Context(device=local, seed=99, substream_block=rank) as ctx:
+        handle = [ctx.xgpu_create(n, world) if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            ctx.xgpu_open(handle[0], n, world)
+        dist.barrier()
+        fused = []
+        for rep in range(2):                                  # twice: the arrival counters must reset themselves
+            ctx.set_seed(99, rank)
+            ctx.price_xgpu_device(n, ptrs, 100.0, float(local_trials), rank, float(total_paths), trials, stream=stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            fused.append(ctx.xgpu_results(n))
+            dist.barrier()
+        ctx.xgpu_close()
+        dist.barrier()
+    same = [None] * world
+    dist.all_gather_object(same, [fused[0]["call"].tolist(), fused[0]["call_se"].tolist()])
+    out["trials_minor_fused"] = dict(call=fused[0]["call"].tolist(), put=fused[0]["put"].tolist(),
+                                     call_se=fused[0]["call_se"].tolist(), put_se=fused[0]["put_se"].tolist(),
+                                     repeat_equal=bool(all(np.array_equal(fused[0][k], fused[1][k]) for k in fused[0])),
+                                     same_on_all_ranks=all(s == same[0] for s in same))
     if rank == 0:
         print("MULTIGPU_JSON " + json.dumps(out), flush=True)
     dist.barrier()

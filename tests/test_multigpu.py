@@ -48,3 +48,10 @@ def test_two_gpu_sharding(oracle):
             exact = oracle.bs64(name, float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
             assert abs(tm[key][k] - exact) <= 3.5 * tm[key + "_se"][k] + 1e-4
         assert tm["call_se"][k] < 0.04              # full-sample SE: sigma_payoff (<= ~22) / sqrt(4e5)
+
+    # the fused cross-GPU combine (peer memory + cross-GPU arrival counters, no NCCL on the data path) uses the same
+    # seeds and the same trial split: with two ranks the rank-ordered sum equals the all-reduce bit for bit
+    fu = out["trials_minor_fused"]
+    assert fu["repeat_equal"] and fu["same_on_all_ranks"]
+    for key in ("call", "put", "call_se", "put_se"):
+        assert fu[key] == tm[key], key
