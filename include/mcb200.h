@@ -141,7 +141,11 @@ int mcb200_greeks_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free
  *   owner : mcb200_xgpu_create(ctx, n_max, world, 0, handle)      -> ship the 64 handle bytes to the other ranks
  *   others: mcb200_xgpu_open(ctx, handle, n_max, world, 0)
  *   all   : mcb200_price_xgpu_device(..., num_trials_local, flags, rank, total_paths, total_num_trials, stream)
- *   all   : synchronize the stream, barrier across ranks, then mcb200_xgpu_results(ctx, n, call, put, call_se, put_se) */
+ *   all   : mcb200_xgpu_results(ctx, n, call, put, call_se, put_se)  -- waits ON THE DEVICE (a one-thread kernel spinning
+ *           on the buffer's epoch word) until the round is complete on every rank, then copies the results out.
+ * Every rank must issue the same sequence of mcb200_price_xgpu_device calls (the round number is counted locally).
+ * The kernel of mcb200_price_xgpu_device is enqueued on `cuda_stream`; the wait and the copy run on the context's
+ * own stream behind an event recorded after that kernel. */
 #define MCB200_IPC_HANDLE_BYTES 64
 int mcb200_xgpu_create(mcb200_ctx *ctx, int n_max, int world, int greeks, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES]);
 int mcb200_xgpu_open(mcb200_ctx *ctx, const uint8_t handle[MCB200_IPC_HANDLE_BYTES], int n_max, int world, int greeks);

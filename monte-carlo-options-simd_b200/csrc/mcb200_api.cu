@@ -87,6 +87,9 @@ struct mcb200_ctx {
     float* h_stage_dev = nullptr;  // device-side address of h_stage: small batches write their results straight to it
     // cross-GPU exchange buffer (trials-sharded fused combine): owned (cudaMalloc) or opened through CUDA IPC
     void* xg_base = nullptr; bool xg_owner = false; int xg_world = 0, xg_n_max = 0, xg_n_acc = 0;
+    unsigned xg_epoch = 0;        // rounds launched through the exchange buffer (all ranks call in lockstep)
+    int* xg_status = nullptr;     // device word written by xgpu_wait_kernel
+    cudaEvent_t xg_event = nullptr;   // recorded behind the latest xgpu launch (it may sit on a caller stream)
     uint64_t launches = 0;
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -209,6 +212,8 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->xg_base) { if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base); }
+    if (c->xg_status) cudaFree(c->xg_status);
+    if (c->xg_event) cudaEventDestroy(c->xg_event);
     delete c;
 }
 
@@ -248,13 +253,14 @@ struct Request {
 };
 
 // Exchange buffer layout on the owner GPU: [world][n_max][n_acc] fp64 rows | [2 * n_est][n_max] f32 results | [n_max] u32
-struct XgLayout { double* slots; float* results; unsigned* arrivals; size_t bytes; };
+struct XgLayout { double* slots; float* results; unsigned* arrivals; unsigned* ctl; size_t bytes; };
 static XgLayout xg_layout_for(void* base, int world, int n_max, int n_acc) {
     XgLayout L;
     char* p = (char*)base;
     L.slots = (double*)p; p += sizeof(double) * (size_t)world * n_max * n_acc;
     L.results = (float*)p; p += sizeof(float) * (size_t)n_acc * n_max;
     L.arrivals = (unsigned*)p; p += sizeof(unsigned) * (size_t)n_max;
+    L.ctl = (unsigned*)p; p += sizeof(unsigned) * 4;
     L.bytes = (size_t)(p - (char*)base);
     return L;
 }
@@ -323,7 +329,8 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.growth_out = rq.growth_out;
     if (rq.xg) {
         XgLayout L = xg_layout(c);
-        a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_rank = rq.xg_rank; a.xg_world = c->xg_world;
+        a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_ctl = L.ctl; a.xg_epoch = c->xg_epoch;
+        a.xg_rank = rq.xg_rank; a.xg_world = c->xg_world;
         a.xg_n_max = c->xg_n_max;
         a.fin.n_paths = rq.xg_total_paths; a.fin.num_trials = rq.xg_total_trials;
     }
@@ -477,7 +484,7 @@ static int xg_release(mcb200_ctx* c) {
         cudaStreamSynchronize(c->stream);
         if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base);
     }
-    c->xg_base = nullptr; c->xg_owner = false; c->xg_world = c->xg_n_max = c->xg_n_acc = 0;
+    c->xg_base = nullptr; c->xg_owner = false; c->xg_world = c->xg_n_max = c->xg_n_acc = 0; c->xg_epoch = 0;
     return MCB200_OK;
 }
 
@@ -537,23 +544,46 @@ extern "C" int mcb200_price_xgpu_device(mcb200_ctx* c, int n, const float* spot,
     rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials_local;
     rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
     rq.xg = true; rq.xg_rank = rank; rq.xg_total_paths = total_paths; rq.xg_total_trials = total_num_trials;
+    ++c->xg_epoch;                        // every rank launches the same rounds in the same order
     const XgLayout L = xg_layout(c);
     float* out[2] = {L.results, L.results + c->xg_n_max};
     float* se[2] = {L.results + 2 * (size_t)c->xg_n_max, L.results + 3 * (size_t)c->xg_n_max};
-    return run_sim(c, rq, nullptr, true, out, se, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, nullptr);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    rc = run_sim(c, rq, nullptr, true, out, se, st, nullptr);
+    if (rc) return rc;
+    if (!c->xg_event) CU(cudaEventCreateWithFlags(&c->xg_event, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->xg_event, st));
+    return MCB200_OK;
 }
 
-// Copy the combined results out of the exchange buffer (peer read on non-owner ranks).  The caller must have
-// synchronised ALL ranks' launches first (stream synchronize + a barrier).
+// Wait (on the device, no collective) until the latest round is complete on ALL ranks, then copy the combined results
+// out of the exchange buffer (a peer read on non-owner ranks).
 extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float* put_out, float* call_se, float* put_se) {
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     if (!c->xg_base || n < 0 || n > c->xg_n_max) return fail(MCB200_ERR_INVALID, "xgpu_results: no exchange buffer or bad n");
+    if (c->xg_epoch == 0) return fail(MCB200_ERR_INVALID, "xgpu_results: nothing was launched through the exchange buffer");
     const XgLayout L = xg_layout(c);
+    if (!c->xg_status) CU(cudaMalloc((void**)&c->xg_status, sizeof(int)));
+    const size_t out_f = 4 * (size_t)c->xg_n_max;
+    int rc = ensure_stage(c, out_f + 16);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    // the wait kernel must not share the GPU with this rank's own path kernel (it would take a CTA slot from it)
+    if (c->xg_event) CU(cudaStreamWaitEvent(st, c->xg_event, 0));
+    xgpu_wait_kernel<<<1, 1, 0, st>>>(L.ctl, c->xg_epoch, 20ull * 1000 * 1000 * 1000, c->xg_status);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_stage, L.results, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_stage + out_f, c->xg_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int ok = 0;
+    std::memcpy(&ok, c->h_stage + out_f, sizeof(int));
+    if (!ok) return fail(MCB200_ERR_CUDA, "xgpu_results: round %u was not completed by all ranks within 20 s", c->xg_epoch);
     float* dst[4] = {call_out, put_out, call_se, put_se};
     for (int k = 0; k < 4; ++k)
-        if (dst[k] && n > 0) CU(cudaMemcpy(dst[k], L.results + (size_t)k * c->xg_n_max, sizeof(float) * n, cudaMemcpyDeviceToHost));
+        if (dst[k] && n > 0) std::memcpy(dst[k], c->h_stage + (size_t)k * c->xg_n_max, sizeof(float) * n);
     return MCB200_OK;
 }
 

@@ -71,6 +71,9 @@ struct SimArgs {
     // the count sums the rows in rank order and finalises into the exchange buffer.  Null xg_slots = single-GPU launch.
     double* xg_slots;        // [xg_world][xg_n_max][2 * kEst] on the owner GPU
     unsigned* xg_arrivals;   // [xg_n_max] on the owner GPU, zero between launches
+    unsigned* xg_ctl;        // owner GPU: [0] = options finalised in this launch round (self-resetting), [1] = epoch of
+                             // the last COMPLETE round, published by the warp that finalises the round's last option
+    unsigned xg_epoch;       // this round's epoch (same on every rank)
     int xg_rank, xg_world, xg_n_max;
     float inline_opt[6][kInlineMaxOptions];     // spot, strike, vol, rate, years, div
 };
@@ -374,12 +377,39 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                                            a.use_inline ? a.inline_opt[4][o] : a.opt.years[o]);
                 }
                 if (lane == 0) a.arrivals[o] = 0u;           // leave the counter clean for the next launch
+                if (a.xg_slots && finish) {
+                    // results of option o are in the exchange buffer: count it; the last one publishes the epoch that
+                    // every rank's xgpu_wait_kernel is spinning on
+                    __threadfence_system();
+                    __syncwarp();
+                    if (lane == 0 && atomicAdd_system(a.xg_ctl, 1u) == (unsigned)a.n_options - 1u) {
+                        *(volatile unsigned*)a.xg_ctl = 0u;
+                        __threadfence_system();
+                        *(volatile unsigned*)(a.xg_ctl + 1) = a.xg_epoch;
+                    }
+                }
             }
         }
         if (option_done) { ++o; k = 0; enter = true; fresh = true; }
         else { enter = false; fresh = false; }
     }
     if (STREAM == STREAM_FAST) xoshiro_store(g, a.pool + 4ull * gtid);
+}
+
+// Device-side completion wait of the cross-GPU fused combine: one thread spins on the epoch word of the exchange
+// buffer (peer memory) until the round `epoch` is complete on ALL ranks; work queued behind it on the stream (the copy
+// of the results) then sees the whole sample.  Gives up after ~timeout_ns and reports through *status.
+__global__ void xgpu_wait_kernel(const unsigned* ctl, unsigned epoch, unsigned long long timeout_ns, int* status) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    int ok = 1;
+    while (*(volatile const unsigned*)(ctl + 1) != epoch) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { ok = 0; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+    *status = ok;
 }
 
 // ------------------------------------------------------------------------------------------------ closed form

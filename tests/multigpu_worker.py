@@ -21,7 +21,12 @@ def main():
     pkg = importlib.import_module("monte-carlo-options-simd_b200")
     sh = pkg.sharding
     out = {}
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit stream: the library reads a NULL stream as "the context's own stream", which is NOT ordered with
+    # torch's default stream where the all-reduce would run
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # ---- options-major: each rank prices its contiguous block on its own long_jump substream block, no collective on
     #      the data path; the blocks are gathered only to be checked
@@ -73,10 +78,7 @@ def main():
         for rep in range(2):                                  # twice: the arrival counters must reset themselves
             ctx.set_seed(99, rank)
             ctx.price_xgpu_device(n, ptrs, 100.0, float(local_trials), rank, float(total_paths), trials, stream=stream)
-            torch.cuda.synchronize()
-            dist.barrier()
-            fused.append(ctx.xgpu_results(n))
-            dist.barrier()
+            fused.append(ctx.xgpu_results(n))                 # waits on the device for ALL ranks, no barrier needed
         ctx.xgpu_close()
         dist.barrier()
     same = [None] * world
