@@ -155,6 +155,13 @@ int mcb200_price_xgpu_device(mcb200_ctx *ctx, int n, const float *spot, const fl
                              float steps, float num_trials_local, unsigned flags, int rank, double total_paths,
                              double total_num_trials, void *cuda_stream);
 int mcb200_xgpu_results(mcb200_ctx *ctx, int n, float *call_out, float *put_out, float *call_se, float *put_se);
+/* the same for the ten Greek estimators (exchange buffer created / opened with greeks = 1) */
+int mcb200_greeks_xgpu_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
+                              const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
+                              float steps, float num_trials_local, const mcb200_bumps *bumps, int rank,
+                              double total_paths, double total_num_trials, void *cuda_stream);
+int mcb200_xgpu_results_greeks(mcb200_ctx *ctx, int n, float *const out[MCB200_N_GREEK_OUTPUTS],
+                               float *const out_se[MCB200_N_GREEK_OUTPUTS]);
 
 /* ------------------------------------------------------------------ closed form (analytic companion) ----------- */
 /* Black-Scholes closed form with dividend yield for a batch -- the analytic value the reference's tests compare every

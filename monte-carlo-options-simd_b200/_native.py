@@ -110,6 +110,11 @@ def lib():
                                                                            C.c_double, _vp])
     L.mcb200_xgpu_results.restype = C.c_int
     L.mcb200_xgpu_results.argtypes = [_vp, C.c_int] + [_fp] * 4
+    L.mcb200_greeks_xgpu_device.restype = C.c_int
+    L.mcb200_greeks_xgpu_device.argtypes = ([_vp, C.c_int] + [_vp] * 6 + [_f, _f, C.POINTER(Bumps), C.c_int, C.c_double,
+                                                                            C.c_double, _vp])
+    L.mcb200_xgpu_results_greeks.restype = C.c_int
+    L.mcb200_xgpu_results_greeks.argtypes = [_vp, C.c_int, _GreekOut, _GreekOut]
     L.mcb200_bs_batch.restype = C.c_int
     L.mcb200_bs_batch.argtypes = [_vp, C.c_int] + six + [_GreekOut]
     L.mcb200_bs_batch_device.restype = C.c_int

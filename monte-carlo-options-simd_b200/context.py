@@ -251,6 +251,22 @@ class Context:
                                                  N.ANTITHETIC if antithetic else 0, int(rank), float(total_paths),
                                                  float(total_num_trials), C.c_void_p(stream)))
 
+    def greeks_xgpu_device(self, n, in_ptrs, steps, num_trials_local, bumps, rank, total_paths, total_num_trials,
+                           stream=0):
+        b = N.Bumps(*bumps)
+        N.check(N.lib().mcb200_greeks_xgpu_device(self._h, n, *[C.c_void_p(p) for p in in_ptrs], steps, num_trials_local,
+                                                  C.byref(b), int(rank), float(total_paths), float(total_num_trials),
+                                                  C.c_void_p(stream)))
+
+    def xgpu_results_greeks(self, n):
+        vals = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        ses = [np.empty(n, np.float32) for _ in range(N.N_GREEK_OUTPUTS)]
+        N.check(N.lib().mcb200_xgpu_results_greeks(self._h, n, N._GreekOut(*[N.fptr(v) for v in vals]),
+                                                   N._GreekOut(*[N.fptr(s) for s in ses])))
+        res = {name: vals[i] for i, name in enumerate(N.GREEK_NAMES)}
+        res.update({name + "_se": ses[i] for i, name in enumerate(N.GREEK_NAMES)})
+        return res
+
     def xgpu_results(self, n):
         out = [np.empty(n, np.float32) for _ in range(4)]
         N.check(N.lib().mcb200_xgpu_results(self._h, n, *[N.fptr(o) for o in out]))

@@ -556,17 +556,51 @@ extern "C" int mcb200_price_xgpu_device(mcb200_ctx* c, int n, const float* spot,
     return MCB200_OK;
 }
 
-// Wait (on the device, no collective) until the latest round is complete on ALL ranks, then copy the combined results
-// out of the exchange buffer (a peer read on non-owner ranks).
-extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float* put_out, float* call_se, float* put_se) {
-    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+extern "C" int mcb200_greeks_xgpu_device(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
+                                         const float* rate, const float* years, const float* div, float steps,
+                                         float num_trials_local, const mcb200_bumps* bumps, int rank, double total_paths,
+                                         double total_num_trials, void* cuda_stream) {
+    const float* in[6] = {spot, strike, vol, rate, years, div};
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (!bumps) return fail(MCB200_ERR_INVALID, "null bumps");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    if (!c->xg_base || n < 0 || n > c->xg_n_max) return fail(MCB200_ERR_INVALID, "xgpu_results: no exchange buffer or bad n");
+    if (!c->xg_base) return fail(MCB200_ERR_INVALID, "no exchange buffer: call mcb200_xgpu_create / mcb200_xgpu_open first");
+    if (n > c->xg_n_max || rank < 0 || rank >= c->xg_world || c->xg_n_acc != 2 * EST_COUNT_GREEKS)
+        return fail(MCB200_ERR_INVALID, "xgpu (greeks): n=%d (max %d), rank=%d (world %d), buffer created for %d sums",
+                    n, c->xg_n_max, rank, c->xg_world, c->xg_n_acc);
+    mcb200_plan pl;
+    if (make_plan(n, steps, num_trials_local, c->grid_slots, &pl) != MCB200_OK || pl.n_paths == 0)
+        return fail(MCB200_ERR_INVALID, "xgpu: every rank must simulate at least 8 trials (steps=%g trials=%g)", steps, num_trials_local);
+    Request rq;
+    rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials_local;
+    rq.payoff = PAYOFF_GREEKS; rq.bumps = to_bumps(bumps);
+    rq.xg = true; rq.xg_rank = rank; rq.xg_total_paths = total_paths; rq.xg_total_trials = total_num_trials;
+    ++c->xg_epoch;
+    const XgLayout L = xg_layout(c);
+    float* out[EST_COUNT_GREEKS]; float* se[EST_COUNT_GREEKS];
+    for (int e = 0; e < EST_COUNT_GREEKS; ++e) {
+        out[e] = L.results + (size_t)e * c->xg_n_max;
+        se[e] = L.results + (size_t)(EST_COUNT_GREEKS + e) * c->xg_n_max;
+    }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    rc = run_sim(c, rq, nullptr, true, out, se, st, nullptr);
+    if (rc) return rc;
+    if (!c->xg_event) CU(cudaEventCreateWithFlags(&c->xg_event, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->xg_event, st));
+    return MCB200_OK;
+}
+
+// Wait (on the device, no collective) until the latest round is complete on ALL ranks, then copy the combined results
+// out of the exchange buffer (a peer read on non-owner ranks): rows [value e][n_max] then [SE e][n_max].
+static int xg_fetch(mcb200_ctx* c, int n, int n_est, float* const* out, float* const* out_se) {
+    if (!c->xg_base || n < 0 || n > c->xg_n_max || c->xg_n_acc != 2 * n_est)
+        return fail(MCB200_ERR_INVALID, "xgpu_results: no matching exchange buffer or bad n");
     if (c->xg_epoch == 0) return fail(MCB200_ERR_INVALID, "xgpu_results: nothing was launched through the exchange buffer");
     const XgLayout L = xg_layout(c);
     if (!c->xg_status) CU(cudaMalloc((void**)&c->xg_status, sizeof(int)));
-    const size_t out_f = 4 * (size_t)c->xg_n_max;
+    const size_t out_f = (size_t)c->xg_n_acc * c->xg_n_max;
     int rc = ensure_stage(c, out_f + 16);
     if (rc) return rc;
     cudaStream_t st = c->stream;
@@ -581,10 +615,28 @@ extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float*
     int ok = 0;
     std::memcpy(&ok, c->h_stage + out_f, sizeof(int));
     if (!ok) return fail(MCB200_ERR_CUDA, "xgpu_results: round %u was not completed by all ranks within 20 s", c->xg_epoch);
-    float* dst[4] = {call_out, put_out, call_se, put_se};
-    for (int k = 0; k < 4; ++k)
-        if (dst[k] && n > 0) std::memcpy(dst[k], c->h_stage + (size_t)k * c->xg_n_max, sizeof(float) * n);
+    for (int e = 0; e < n_est; ++e) {
+        if (out && out[e] && n > 0) std::memcpy(out[e], c->h_stage + (size_t)e * c->xg_n_max, sizeof(float) * n);
+        if (out_se && out_se[e] && n > 0) std::memcpy(out_se[e], c->h_stage + (size_t)(n_est + e) * c->xg_n_max, sizeof(float) * n);
+    }
     return MCB200_OK;
+}
+
+extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float* put_out, float* call_se, float* put_se) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    float* out[2] = {call_out, put_out};
+    float* se[2] = {call_se, put_se};
+    return xg_fetch(c, n, EST_COUNT_PRICE, out, se);
+}
+
+extern "C" int mcb200_xgpu_results_greeks(mcb200_ctx* c, int n, float* const out[MCB200_N_GREEK_OUTPUTS],
+                                          float* const out_se[MCB200_N_GREEK_OUTPUTS]) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return xg_fetch(c, n, EST_COUNT_GREEKS, out, out_se);
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer entry points

@@ -87,6 +87,33 @@ def main():
                                      call_se=fused[0]["call_se"].tolist(), put_se=fused[0]["put_se"].tolist(),
                                      repeat_equal=bool(all(np.array_equal(fused[0][k], fused[1][k]) for k in fused[0])),
                                      same_on_all_ranks=all(s == same[0] for s in same))
+    # ---- the same for the Greeks: fused cross-GPU combine vs moments + all_reduce + finalize on the same seeds
+    bumps = (0.01, 0.01, 0.01, 0.001)
+    gmom = torch.zeros(n, 20, dtype=torch.float64, device=dev)
+    gv, gs = torch.zeros(10, n, device=dev), torch.zeros(10, n, device=dev)
+    g_trials = 80000.0
+    g_local, g_total = sh.partition_trials(g_trials, world, rank)
+    with pkg.Context(device=local, seed=123, substream_block=rank) as ctx:
+        ctx.greeks_moments_device(n, ptrs, 100.0, float(g_local), bumps, gmom.data_ptr(), stream=stream)
+        sh.combine_moments(gmom)
+        ctx.greeks_finalize_device(n, cols[3].data_ptr(), cols[4].data_ptr(), gmom.data_ptr(), float(g_total), g_trials, bumps,
+                                   [gv[i].data_ptr() for i in range(10)], [gs[i].data_ptr() for i in range(10)], stream=stream)
+        torch.cuda.synchronize()
+        handle = [ctx.xgpu_create(n, world, greeks=True) if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            ctx.xgpu_open(handle[0], n, world, greeks=True)
+        dist.barrier()
+        ctx.set_seed(123, rank)
+        ctx.greeks_xgpu_device(n, ptrs, 100.0, float(g_local), bumps, rank, float(g_total), g_trials, stream=stream)
+        gf = ctx.xgpu_results_greeks(n)
+        dist.barrier()
+        ctx.xgpu_close()
+    names = pkg.GREEK_NAMES
+    out["greeks_fused_equals_nccl"] = bool(all(np.array_equal(gf[nm], gv[i].cpu().numpy()) and
+                                               np.array_equal(gf[nm + "_se"], gs[i].cpu().numpy())
+                                               for i, nm in enumerate(names)))
+    out["greeks_fused_gamma"] = gf["gamma"].tolist()
     if rank == 0:
         print("MULTIGPU_JSON " + json.dumps(out), flush=True)
     dist.barrier()

@@ -55,3 +55,4 @@ def test_two_gpu_sharding(oracle):
     assert fu["repeat_equal"] and fu["same_on_all_ranks"]
     for key in ("call", "put", "call_se", "put_se"):
         assert fu[key] == tm[key], key
+    assert out["greeks_fused_equals_nccl"] and all(g > 0 for g in out["greeks_fused_gamma"])
