@@ -313,16 +313,22 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
             slot[lane] = mine;
         }
         if (segment_done) {
-            // publish the slot and count the arrival; the warp that completes the option finishes it
-            __threadfence();
-            __syncwarp();
             const long long first_round = (long long)o * a.rounds_per_option;
             const int w_first = owner_warp(first_round, R, W);
             const int w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
-            unsigned prev = 0;
-            if (lane == 0) prev = atomicAdd(a.arrivals + o, 1u);
-            prev = __shfl_sync(0xffffffffu, prev, 0);
-            if ((int)prev == w_last - w_first) {
+            const bool solo = (w_first == w_last);           // the whole option lives in this warp's range
+            bool complete = solo;
+            double s = mine;                                 // lane i < kAcc holds accumulator i
+            if (!solo) {
+                // publish the slot and count the arrival; the warp that completes the option finishes it
+                __threadfence();
+                __syncwarp();
+                unsigned prev = 0;
+                if (lane == 0) prev = atomicAdd(a.arrivals + o, 1u);
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                complete = ((int)prev == w_last - w_first);
+            }
+            if (complete && !solo) {
                 __threadfence();
                 // Fixed-order sum of the option's segments.  Lane l = (group, accumulator): kGroups groups stride over
                 // the segments with independent loads in flight (a serial walk would expose one L2 round trip per
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 constexpr int kGroups = 32 / kAccPad;
                 const int i = lane % kAccPad, grp = lane / kAccPad;
                 const int n_seg = w_last - w_first + 1;
-                double s = 0.0;
+                s = 0.0;
                 if (i < kAcc) {
                     const double* base = a.slots + ((size_t)w_first + (size_t)o) * kAcc + i;
                     int j = grp;
@@ -346,6 +352,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 }
 #pragma unroll
                 for (int off = kAccPad; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0) a.arrivals[o] = 0u;           // leave the counter clean for the next launch
+            }
+            if (complete) {
                 if (a.moments_out && lane < kAcc) a.moments_out[(size_t)o * kAcc + lane] = s;
                 bool finish = a.finalize != 0;
                 if (a.xg_slots) {
@@ -376,7 +385,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                         finalize_estimator(a.fin, o, lane, sum, sq, a.use_inline ? a.inline_opt[3][o] : a.opt.rate[o],
                                            a.use_inline ? a.inline_opt[4][o] : a.opt.years[o]);
                 }
-                if (lane == 0) a.arrivals[o] = 0u;           // leave the counter clean for the next launch
                 if (a.xg_slots && finish) {
                     // results of option o are in the exchange buffer: count it; the last one publishes the epoch that
                     // every rank's xgpu_wait_kernel is spinning on
