@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     if not (force or stale()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc(), "-ccbin", HOST_CXX, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall",
+    extra = os.environ.get("MCB200_NVCC_FLAGS", "").split()          # tuning experiments only (e.g. -DMCB_QUAD_UNROLL=4)
+    cmd = [nvcc(), "-ccbin", HOST_CXX, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall", *extra,
            "-shared", "-cudart", "static", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -13,7 +13,13 @@ constexpr int kWarps = kThreads / 32;
 // Resident CTAs per SM the path kernels are compiled for: 4 x 256 threads = 64 registers per thread.  The inner step
 // is bound by the ALU pipe, not by latency: measured 3.32 pairs/clk/SM at 8 CTAs/SM and 3.32 at 4 with unroll 8
 // (profiles/r1_microbench_v2_pipes.json), so half occupancy costs nothing and buys register-resident accumulators.
-constexpr int kMinCtasPerSm = 4;
+#ifndef MCB_MIN_CTAS
+#define MCB_MIN_CTAS 4
+#endif
+#ifndef MCB_QUAD_UNROLL
+#define MCB_QUAD_UNROLL 2
+#endif
+constexpr int kMinCtasPerSm = MCB_MIN_CTAS;
 constexpr int kInlineMaxOptions = 128;      // host batches up to this size travel in the launch parameters (3 KB)
 constexpr int kMaxRoundsPerFlush = 4096;   // paths a thread sums in fp32 before its moments go to fp64
 
