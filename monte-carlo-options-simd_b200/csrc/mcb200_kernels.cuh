@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 if (STREAM == STREAM_FAST) {
                     // four pairs per three generator outputs, then the 0..3 left-over pairs one output each
                     const int quads = a.half_steps >> 2;
-#pragma unroll MCB_QUAD_UNROLL
+#pragma unroll kQuadUnroll
                     for (int i = 0; i < quads; ++i) m = quad_fast(g, m);
                     for (int i = quads << 2; i < a.half_steps; ++i) m = pair_fast(g, m);
                 } else {

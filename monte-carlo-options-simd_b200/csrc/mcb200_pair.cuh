@@ -20,6 +20,7 @@ constexpr int kWarps = kThreads / 32;
 #define MCB_QUAD_UNROLL 2
 #endif
 constexpr int kMinCtasPerSm = MCB_MIN_CTAS;
+constexpr int kQuadUnroll = MCB_QUAD_UNROLL;     // quads per iteration of the path loop (8 pairs at the default 2)
 constexpr int kInlineMaxOptions = 128;      // host batches up to this size travel in the launch parameters (3 KB)
 constexpr int kMaxRoundsPerFlush = 4096;   // paths a thread sums in fp32 before its moments go to fp64
 
