@@ -37,8 +37,8 @@ typedef enum {
 #define MCB200_ANTITHETIC 1u    /* call_price_av / put_price_av estimator (mc_simd.rs:82-149) */
 
 /* ------------------------------------------------------------------ context ------------------------------------ */
-/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per resident thread:
- * sm_count * ctas_per_sm * 256).
+/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per resident thread of
+ * the price kernels: sm_count * ctas_per_sm * 256; the Greeks kernel uses the first grid_slots_greeks * 256 of them).
  * Thread slot i of the device uses substream jump^i(long_jump^substream_block(splitmix64(seed))): 2^128 draws per
  * thread, 2^64 thread slots per block, one block per GPU/rank (replaces per-chunk OS-entropy seeding,
  * mc_simd.rs:52-54).  Launches continue their substreams, so a fixed (seed, block, call sequence) is reproducible
@@ -50,7 +50,8 @@ const char *mcb200_last_error(void);
 
 typedef struct {
     int device, sm_count, ctas_per_sm, threads_per_cta;
-    int grid_slots;              /* resident CTAs the planner fills: sm_count * ctas_per_sm (4 x 256 threads per SM) */
+    int grid_slots;              /* resident CTAs the planner fills for the price kernels: sm_count * ctas_per_sm (4) */
+    int grid_slots_greeks;       /* ... and for the Greeks kernel, which runs 3 fatter CTAs per SM */
     int64_t pool_threads;        /* generator states held in HBM (32 bytes each) */
     uint64_t kernel_launches;    /* kernels launched by this context so far */
     uint64_t seed;

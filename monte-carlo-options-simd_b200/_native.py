@@ -28,7 +28,7 @@ class Mcb200Error(RuntimeError):
 
 class Info(C.Structure):
     _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("ctas_per_sm", C.c_int), ("threads_per_cta", C.c_int),
-                ("grid_slots", C.c_int), ("pool_threads", C.c_int64), ("kernel_launches", C.c_uint64),
+                ("grid_slots", C.c_int), ("grid_slots_greeks", C.c_int), ("pool_threads", C.c_int64), ("kernel_launches", C.c_uint64),
                 ("seed", C.c_uint64), ("substream_block", C.c_uint32), ("sm_clock_khz", C.c_int)]
 
 

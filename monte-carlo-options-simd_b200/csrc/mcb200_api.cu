@@ -71,8 +71,9 @@ using namespace mcb200;
 struct mcb200_ctx {
     int device = 0;
     int sm_count = 0;
-    int ctas_per_sm = 0;          // resident 256-thread CTAs per SM the planner assumes (min over kernel variants used)
-    int grid_slots = 0;
+    int ctas_per_sm = 0;          // resident 256-thread CTAs per SM of the price / antithetic kernels
+    int grid_slots = 0;           // ... and the CTAs the planner fills for them
+    int grid_slots_greeks = 0;    // the Greeks kernel runs at fewer, fatter CTAs per SM (mcb200_pair.cuh)
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
     uint64_t seed = 0;
@@ -182,12 +183,13 @@ extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, ui
         if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_AV, false>, &occ_av))) break;
         if ((rc = occupancy(simulate_kernel<STREAM_FAST, PAYOFF_GREEKS, false>, &occ_greeks))) break;
         int occ = occ_price < occ_av ? occ_price : occ_av;
-        if (occ_greeks < occ) occ = occ_greeks;
-        if (occ < 1) { rc = fail(MCB200_ERR_CUDA, "kernel occupancy query returned %d", occ); break; }
-        if (occ > kMinCtasPerSm) occ = kMinCtasPerSm;     // the design point (mcb200_pair.cuh); more residency buys nothing
+        if (occ < 1 || occ_greeks < 1) { rc = fail(MCB200_ERR_CUDA, "kernel occupancy query returned %d / %d", occ, occ_greeks); break; }
+        if (occ > kPriceCtasPerSm) occ = kPriceCtasPerSm;         // the design points (mcb200_pair.cuh); more residency buys nothing
+        if (occ_greeks > kGreeksCtasPerSm) occ_greeks = kGreeksCtasPerSm;
         c->ctas_per_sm = occ;
         c->grid_slots = c->sm_count * occ;
-        c->pool_threads = (int64_t)c->grid_slots * kThreads;
+        c->grid_slots_greeks = c->sm_count * occ_greeks;
+        c->pool_threads = (int64_t)(c->grid_slots > c->grid_slots_greeks ? c->grid_slots : c->grid_slots_greeks) * kThreads;
         if (cudaMalloc((void**)&c->pool, (size_t)c->pool_threads * 32) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "pool alloc failed"); break; }
         if (cudaMalloc((void**)&c->d_jump, sizeof(XOSHIRO256_JUMP_POW2)) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "jump table alloc failed"); break; }
         if (cudaMemcpy(c->d_jump, XOSHIRO256_JUMP_POW2, sizeof(XOSHIRO256_JUMP_POW2), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "jump table copy failed"); break; }
@@ -230,7 +232,8 @@ extern "C" const char* mcb200_last_error(void) { return g_err; }
 extern "C" int mcb200_ctx_info(mcb200_ctx* c, mcb200_info* out) {
     if (!c || !out) return fail(MCB200_ERR_INVALID, "null argument");
     out->device = c->device; out->sm_count = c->sm_count; out->ctas_per_sm = c->ctas_per_sm;
-    out->threads_per_cta = kThreads; out->grid_slots = c->grid_slots; out->pool_threads = c->pool_threads;
+    out->threads_per_cta = kThreads; out->grid_slots = c->grid_slots; out->grid_slots_greeks = c->grid_slots_greeks;
+    out->pool_threads = c->pool_threads;
     out->kernel_launches = c->launches; out->seed = c->seed; out->substream_block = c->block;
     out->sm_clock_khz = c->clock_khz;
     return MCB200_OK;
@@ -299,7 +302,7 @@ static int run_finalize(mcb200_ctx* c, int n, int n_est, const double* moments, 
 static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool finalize, float* const* out,
                    float* const* out_se, cudaStream_t st, mcb200_plan* plan_out) {
     mcb200_plan pl;
-    int rc = make_plan(rq.n, rq.steps, rq.num_trials, c->grid_slots, &pl);
+    int rc = make_plan(rq.n, rq.steps, rq.num_trials, rq.payoff == PAYOFF_GREEKS ? c->grid_slots_greeks : c->grid_slots, &pl);
     if (rc != MCB200_OK) return fail(rc, "invalid request: n=%d steps=%g num_trials=%g", rq.n, rq.steps, rq.num_trials);
     if (plan_out) *plan_out = pl;
     const int n_est = rq.payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
@@ -650,7 +653,7 @@ static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps,
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     mcb200_plan pl;
-    rc = make_plan(n, steps, num_trials, c->grid_slots, &pl);
+    rc = make_plan(n, steps, num_trials, payoff == PAYOFF_GREEKS ? c->grid_slots_greeks : c->grid_slots, &pl);
     if (rc) return fail(rc, "invalid request: n=%d steps=%g num_trials=%g", n, steps, num_trials);
     if (n == 0) return MCB200_OK;
     const int n_est = payoff == PAYOFF_GREEKS ? EST_COUNT_GREEKS : EST_COUNT_PRICE;

@@ -26,8 +26,14 @@ enum Estimator {
     EST_COUNT_PRICE = 2, EST_COUNT_GREEKS = 10
 };
 
-template <int PAYOFF> struct PayoffTraits { static constexpr int kEst = 2; static constexpr int kConst = 4; };
-template <> struct PayoffTraits<PAYOFF_GREEKS> { static constexpr int kEst = 10; static constexpr int kConst = 20; };
+template <int PAYOFF> struct PayoffTraits {
+    static constexpr int kEst = 2; static constexpr int kConst = 4;
+    static constexpr int kCtasPerSm = kPriceCtasPerSm; static constexpr int kQuadUnroll = kPriceQuadUnroll;
+};
+template <> struct PayoffTraits<PAYOFF_GREEKS> {
+    static constexpr int kEst = 10; static constexpr int kConst = 20;
+    static constexpr int kCtasPerSm = kGreeksCtasPerSm; static constexpr int kQuadUnroll = kGreeksQuadUnroll;
+};
 
 struct OptionArrays {          // struct-of-arrays option batch in HBM (f32, n entries each)
     const float* spot; const float* strike; const float* vol; const float* rate; const float* years; const float* div;
@@ -221,11 +227,12 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 //     bit-reproducible, independent of which warp arrives last) and writes moments and/or final values and SEs.
 // Path data never leaves registers.
 template <int STREAM, int PAYOFF, bool DUMP>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) simulate_kernel(const __grid_constant__ SimArgs a) {
     constexpr int kEst = PayoffTraits<PAYOFF>::kEst;
     constexpr int kAcc = 2 * kEst;
     constexpr int kConst = PayoffTraits<PAYOFF>::kConst;
     constexpr bool kConstInSmem = PAYOFF == PAYOFF_GREEKS;
+    constexpr int kQuadUnroll_ = PayoffTraits<PAYOFF>::kQuadUnroll;
     __shared__ float s_const[kConstInSmem ? kWarps * kConst : 1];
 
     const int lane = threadIdx.x & 31;
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) simulate_kernel(const
                 if (STREAM == STREAM_FAST) {
                     // four pairs per three generator outputs, then the 0..3 left-over pairs one output each
                     const int quads = a.half_steps >> 2;
-#pragma unroll kQuadUnroll
+#pragma unroll kQuadUnroll_
                     for (int i = 0; i < quads; ++i) m = quad_fast(g, m);
                     for (int i = quads << 2; i < a.half_steps; ++i) m = pair_fast(g, m);
                 } else {

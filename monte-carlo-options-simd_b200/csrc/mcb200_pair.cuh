@@ -10,17 +10,27 @@ namespace mcb200 {
 
 constexpr int kThreads = 256;          // threads per CTA (8 warps, 2 per SM sub-partition)
 constexpr int kWarps = kThreads / 32;
-// Resident CTAs per SM the path kernels are compiled for: 4 x 256 threads = 64 registers per thread.  The inner step
-// is bound by the ALU pipe, not by latency: measured 3.32 pairs/clk/SM at 8 CTAs/SM and 3.32 at 4 with unroll 8
-// (profiles/r1_microbench_v2_pipes.json), so half occupancy costs nothing and buys register-resident accumulators.
-#ifndef MCB_MIN_CTAS
-#define MCB_MIN_CTAS 4
+// Resident CTAs per SM and quads per loop iteration the path kernels are compiled for.  The inner step is bound by
+// the ALU pipe, not by latency (3.3 pairs/clk/SM at 8, 4 or 2 CTAs/SM alike for pair_fast, profiles/), so low occupancy
+// costs nothing and buys register-resident accumulators.  Measured with tools/tune_unroll_occupancy.sh:
+//   price / antithetic kernels: 4 CTAs/SM (64 registers), 2 quads per iteration   (C2 0.82, C5R 0.97 of the roofline)
+//   Greeks kernel (20 moment registers): 3 CTAs/SM (85 registers), 4 quads per iteration   (C4 0.93 instead of 0.88)
+// The MCB_* macros exist for that sweep only (MCB200_NVCC_FLAGS in build.py).
+#ifndef MCB_PRICE_CTAS
+#define MCB_PRICE_CTAS 4
 #endif
-#ifndef MCB_QUAD_UNROLL
-#define MCB_QUAD_UNROLL 2
+#ifndef MCB_PRICE_UNROLL
+#define MCB_PRICE_UNROLL 2
 #endif
-constexpr int kMinCtasPerSm = MCB_MIN_CTAS;
-constexpr int kQuadUnroll = MCB_QUAD_UNROLL;     // quads per iteration of the path loop (8 pairs at the default 2)
+#ifndef MCB_GREEKS_CTAS
+#define MCB_GREEKS_CTAS 3
+#endif
+#ifndef MCB_GREEKS_UNROLL
+#define MCB_GREEKS_UNROLL 4
+#endif
+constexpr int kPriceCtasPerSm = MCB_PRICE_CTAS, kPriceQuadUnroll = MCB_PRICE_UNROLL;
+constexpr int kGreeksCtasPerSm = MCB_GREEKS_CTAS, kGreeksQuadUnroll = MCB_GREEKS_UNROLL;
+constexpr int kMaxCtasPerSm = kPriceCtasPerSm > kGreeksCtasPerSm ? kPriceCtasPerSm : kGreeksCtasPerSm;
 constexpr int kInlineMaxOptions = 128;      // host batches up to this size travel in the launch parameters (3 KB)
 constexpr int kMaxRoundsPerFlush = 4096;   // paths a thread sums in fp32 before its moments go to fp64
 
