@@ -40,8 +40,9 @@ class Context:
     def set_seed(self, seed, substream_block=0):
         N.check(N.lib().mcb200_ctx_set_seed(self._h, int(seed) & (2 ** 64 - 1), int(substream_block)))
 
-    def plan(self, n_options, steps, num_trials):
-        return plan_query(n_options, steps, num_trials, self.info()["grid_slots"])
+    def plan(self, n_options, steps, num_trials, greeks=False):
+        """Launch plan of a batch on this device (the Greeks kernel runs fewer, fatter CTAs per SM)."""
+        return plan_query(n_options, steps, num_trials, self.info()["grid_slots_greeks" if greeks else "grid_slots"])
 
     def export_states(self, first, count):
         out = np.empty((count, 4), np.uint64)
