@@ -1,13 +1,15 @@
 // mcb200_kernels.cuh -- the fused GBM path + payoff kernels (sm_100a) and their fixed-order second pass.
 //
 // One kernel family replaces the reference's inner step and its six simulation cores:
-//   speed_update                    /root/reference/src/mc_simd.rs:9-21      -> pair_fast() / pair_ref()
+//   speed_update                    /root/reference/src/mc_simd.rs:9-21      -> quad_fast() / pair_fast() / pair_ref()
 //   get_rand_uniform_f32x8          /root/reference/src/rand32x8.rs:5-21     -> uniforms built in pair_*()
 //   monte_carlo_pricing             src/mc_simd.rs:25-79                      -> simulate_kernel<*, PAYOFF_PRICE>
 //   monte_carlo_av_pricing          src/mc_simd.rs:82-149                     -> simulate_kernel<*, PAYOFF_AV>
 //   monte_carlo_{spot,volatility,interest,time}_pricing  src/mc_simd.rs:152-473 -> simulate_kernel<*, PAYOFF_GREEKS>
-//   rayon map/reduce + reduce_add + discount (mc_simd.rs:49-51,71-78)        -> block_reduce() + finalize kernels
-// Path data never leaves registers; per option-slice a CTA writes NACC fp64 partial sums.
+//   rayon map/reduce + reduce_add + discount (mc_simd.rs:49-51,71-78)        -> warp butterfly, per-(warp, option) fp64
+//                                                                               slots, fixed-order sum and finalisation by
+//                                                                               the last-arriving warp, in the same kernel
+// Path data never leaves registers.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -2,6 +2,9 @@
 //
 // Replaces speed_update (/root/reference/src/mc_simd.rs:9-21) and the uniform adapter it calls
 // (/root/reference/src/rand32x8.rs:5-21).  Shared by the path kernels and the pipe microbenchmarks.
+//   quad_fast()  production: three generator outputs -> four pairs (the path loop of the kernels)
+//   pair_fast()  one generator output -> one pair (the 0..3 pairs left over when floor(steps/2) % 4 != 0)
+//   pair_ref()   the reference's own consumption of the stream (parity mode)
 #pragma once
 #include <cstdint>
 #include "mcb200_rng.cuh"
@@ -48,7 +51,7 @@ constexpr float kLog2e = 1.44269504088896340736f;
 constexpr float kSqrt2 = 1.41421356237309504880f;
 constexpr float kSqrt2Ln2 = 1.17741002251547469101f;   // sqrt(2 ln 2)
 
-// Production pair update: ONE generator output -> one Box-Muller pair -> two time steps.
+// One-output pair update: ONE generator output -> one Box-Muller pair -> two time steps.
 //   sqrt(-ln u1) * (sin t + cos t) == sqrt(2 ln 2) * sqrt(-log2 u1) * sin(t + pi/4);  the constant is folded into the
 //   terminal scale, so the loop body is 3 MUFU (LG2, SQRT, SIN) + 4 FP32 + 2 bit-casts + the generator.
 // FMODE selects how the two [1,2) floats are built from the generator output (bit-identical results):
