@@ -131,6 +131,30 @@ def _build_c_client(pkg, tmp_path):
     return exe
 
 
+def _build_cpp_client(pkg, tmp_path):
+    """g++ -std=c++17 against include/mc_simd.hpp (the reference's module surface, name for name)."""
+    import subprocess
+    pkg.build()
+    exe = str(tmp_path / "cpp_client")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "c_client", "cpp_client.cpp"), "-L", libdir, "-lmcb200",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    return exe
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
+def test_cpp_mirror_of_mc_simd_without_gpu(pkg, tmp_path):
+    import subprocess
+    res = subprocess.run([_build_cpp_client(pkg, tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    header = open(os.path.join(ROOT, "include", "mc_simd.hpp")).read()
+    for name in ("call_price", "put_price", "call_price_av", "put_price_av", "call_delta", "put_delta", "gamma", "vega",
+                 "call_rho", "put_rho", "call_theta", "put_theta"):
+        assert re.search(r"inline float %s\(" % name, header), name
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
 def test_plain_c_client_links_and_fails_loudly_without_gpu(pkg, tmp_path):
     import subprocess

@@ -460,10 +460,13 @@ def test_plain_c_client_on_gpu(pkg, tmp_path):
     """The C99 client of include/mcb200.h (tests/c_client/c_abi_client.c) prices through the drop-in and the batched
     entry point: the boundary needs nothing but the header and the shared library."""
     import subprocess
-    from test_abi import _build_c_client
+    from test_abi import _build_c_client, _build_cpp_client
     res = subprocess.run([_build_c_client(pkg, tmp_path), "gpu"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
     assert "c client ok (gpu)" in res.stdout
+    res = subprocess.run([_build_cpp_client(pkg, tmp_path), "gpu"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)       # include/mc_simd.hpp: mc_simd::call_price ...
+    assert "cpp client ok (gpu)" in res.stdout
 
 
 def test_c5_sweep_z_scores_are_standard_normal(ctx):
