@@ -217,7 +217,19 @@ def b200_arm(args, w):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT at the first collective when NCCL_DEBUG is set; stdout must carry the
+        # one JSON line only, so file descriptor 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     pkg = importlib.import_module(PACKAGE)
     ctx = pkg.Context(device=local_rank, seed=SEED, substream_block=rank)
     info0 = ctx.info()
