@@ -576,3 +576,51 @@ def test_greeks_moment_path_equals_fused_path(pkg):
     assert np.all((ratio[4] > 0.5) & (ratio[4] < 2.0))          # gamma: a rare-event average, its sample SE is noisy
     z = ((b_out - a_out) / torch.hypot(a_se, b_se)).cpu().numpy()
     assert np.abs(z).max() < 4.0
+
+
+def test_soak_mixed_batches_share_one_context(pkg, oracle):
+    """Three hundred batches of random shape and kind (price, antithetic, Greeks; 1..700 options; 8..30000 trials; odd
+    and even step counts) through ONE context: the slot / arrival-counter buffers are reused and resized all the time,
+    so a counter that is not left at zero, or a stale slot, would corrupt a later batch.  Every batch is checked
+    against the closed form, and a second context replaying the same sequence must agree bit for bit."""
+    rng = np.random.default_rng(123)
+    shapes = []
+    for _ in range(300):
+        kind = ("price", "av", "greeks")[int(rng.integers(0, 3))]
+        n = int(rng.choice([1, 2, 7, 33, 112, 129, 300, 700]))
+        trials = float(rng.choice([8, 24, 100, 1000, 4096, 10000, 30000]))
+        steps = float(rng.choice([2, 7, 16, 50, 101]))
+        shapes.append((kind, n, trials, steps))
+
+    def run_all(ctx):
+        outs = []
+        for kind, n, trials, steps in shapes:
+            spots = np.linspace(85.0, 135.0, n).astype(np.float32)
+            if kind == "greeks":
+                r = ctx.greeks_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], steps, trials)
+            else:
+                r = ctx.price_batch(spots, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], steps, trials,
+                                    antithetic=(kind == "av"))
+            outs.append(r)
+        return outs
+
+    with pkg.Context(device=0, seed=2025) as a:
+        first = run_all(a)
+        free_a = a.info()["kernel_launches"]
+    with pkg.Context(device=0, seed=2025) as b:
+        second = run_all(b)
+    assert free_a >= 301
+    worst = 0.0
+    for (kind, n, trials, steps), r1, r2 in zip(shapes, first, second):
+        for key in r1:
+            assert np.array_equal(r1[key], r2[key]), (kind, n, trials, steps, key)
+        assert np.all(np.isfinite(r1["call"])) and np.all(np.isfinite(r1["put"]))
+        if int(steps) % 2 == 0 and trials >= 1000:            # odd step counts are under-dispersed by design (quirk)
+            spots = np.linspace(85.0, 135.0, n)
+            exact = np.array([oracle.bs64("call_price", float(s), GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+                              for s in spots[:: max(1, n // 8)]])
+            got, se = r1["call"][:: max(1, n // 8)], r1["call_se"][:: max(1, n // 8)]
+            scale = (8 * (int(trials) // 8)) / trials         # the reference divides by num_trials, not by paths run
+            z = np.abs(got / scale - exact) / np.maximum(se / scale, 0.05 * np.sqrt(1000.0 / trials))
+            worst = max(worst, float(z.max()))
+    assert worst < 6.0, worst
