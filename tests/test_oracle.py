@@ -239,3 +239,39 @@ def test_two_independent_restatements_agree_per_path(oracle, steps, trials, mult
     assert np.max(np.abs(m - c["m"])) <= 2e-5 * max(1.0, float(np.abs(c["m"]).max()))
     assert np.max(np.abs(growth - c["growth"]) / c["growth"]) < 5e-6
     assert float(price) == pytest.approx(c["price"], rel=5e-6, abs=1e-6)
+
+
+def test_two_restatements_agree_on_all_twelve_public_functions(oracle, bs_cases):
+    """Every reference test case of mc_simd.rs:781-907 (all twelve public functions, with their bumps) through both
+    restatements -- oracle/ref_mc.c and oracle/np_restatement.py -- on the same chunk seeds.  Prices agree to f32
+    rounding; the finite differences are the reference's own f32 formulas (price_plus - price_minus) / (2h) etc., whose
+    conditioning is ulp(price) / denominator, so that is the tolerance (a few quanta)."""
+    from oracle import np_restatement as npr
+    done = set()
+    for i, c in enumerate([c for c in bs_cases if c["reference_test"].startswith("mc_simd.rs")]):
+        s, k, v, r, t, q = c["params"]
+        fn, h, steps, trials = c["mc_function"], c["bump"], float(c["steps"]), float(min(c["trials"], 2000))
+        seeds = oracle.chunk_seeds(oracle.n_chunks(trials), 31 + i)
+        if fn in ("call_price", "put_price", "call_price_av", "put_price_av"):
+            args, denom = (s, k, v, r, t, q, steps, trials), 1.0
+        elif fn in ("call_delta", "put_delta", "gamma"):
+            args, denom = (s, h, k, v, r, t, q, steps, trials), (h * h if fn == "gamma" else 2.0 * h)
+        elif fn == "vega":
+            args, denom = (s, k, v, h, r, t, q, steps, trials), 200.0 * h
+        elif fn in ("call_rho", "put_rho"):
+            args, denom = (s, k, v, r, h, t, q, steps, trials), 200.0 * h
+        else:
+            args, denom = (s, k, v, r, t, h, q, steps, trials), 2.0 * h
+        a = oracle.mc(fn, *args, seeds=seeds)
+        b = float(npr.public(fn, *args, seeds=seeds))
+        leg = "put_price" if fn.startswith("put") else "call_price"
+        price = abs(oracle.mc(leg, s, k, v, r, t, q, steps, trials, seeds=seeds))
+        # two sources of f32 noise per leg: the rounding of the price itself, and the rounding of every payoff
+        # spot * growth - strike (an ulp of ~spot, whichever libm computes exp), averaged over the paths
+        n_paths = 8 * (int(trials) // 8)
+        quantum = (6.0 * float(np.spacing(np.float32(max(price, 1e-3))))
+                   + 4.0 * float(np.spacing(np.float32(max(s, k)))) / math.sqrt(n_paths)) / denom
+        assert abs(a - b) <= quantum + 2e-6 * abs(a), (c["reference_test"], fn, a, b, quantum)
+        done.add(fn)
+    assert done == {"call_price", "put_price", "call_price_av", "put_price_av", "call_delta", "put_delta", "gamma", "vega",
+                    "call_rho", "put_rho", "call_theta", "put_theta"}
