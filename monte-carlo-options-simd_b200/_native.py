@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmcb200.so")
+LIB_PATH = os.path.join(HERE, "lib", os.environ.get("MCB200_LIB_NAME", "libmcb200.so"))   # alternate: tuning builds
 
 N_GREEK_OUTPUTS = 10
 GREEK_NAMES = ("call", "put", "call_delta", "put_delta", "gamma", "vega", "call_rho", "put_rho", "call_theta",

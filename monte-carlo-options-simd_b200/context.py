@@ -58,8 +58,8 @@ class Context:
         return ms.value
 
     def microbench(self):
-        buf = (N.PipeRate * 64)()
-        n = N.lib().mcb200_microbench(self._h, buf, 64)
+        buf = (N.PipeRate * 128)()
+        n = N.lib().mcb200_microbench(self._h, buf, 128)
         if n < 0:
             raise N.Mcb200Error(-n, N.last_error())
         return [dict(name=buf[i].name.decode(), ops_per_clk_per_sm=buf[i].ops_per_clk_per_sm,

@@ -92,6 +92,9 @@ struct mcb200_ctx {
     int* xg_status = nullptr;     // device word written by xgpu_wait_kernel
     cudaEvent_t xg_event = nullptr;   // recorded behind the latest xgpu launch (it may sit on a caller stream)
     uint64_t launches = 0;
+#ifdef MCB_TRACE
+    unsigned long long* trace = nullptr;    // device buffer of the timeline build (tools/kernel_timeline.py)
+#endif
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
@@ -329,7 +332,10 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.bumps = rq.bumps; a.pool = c->pool; a.chunk_seeds = rq.chunk_seeds; a.slots = c->slots; a.arrivals = c->arrivals;
     a.moments_out = moments_out; a.finalize = finalize ? 1 : 0;
     a.fin = make_finalize(n_est, (double)pl.n_paths, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out, out_se);
-    a.growth_out = rq.growth_out;
+    a.growth_out = rq.growth_out; a.one = 1u;
+#ifdef MCB_TRACE
+    a.trace = c->trace;
+#endif
     if (rq.xg) {
         XgLayout L = xg_layout(c);
         a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_ctl = L.ctl; a.xg_epoch = c->xg_epoch;
@@ -860,6 +866,15 @@ extern "C" int mcb200_ctx_last_sim_ms(mcb200_ctx* c, float* ms_out) {
     CU(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
     return MCB200_OK;
 }
+
+#ifdef MCB_TRACE
+extern "C" int mcb200_debug_set_trace(mcb200_ctx* c, unsigned long long* device_buf) {
+    if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->trace = device_buf;
+    return MCB200_OK;
+}
+#endif
 
 extern "C" int mcb200_microbench(mcb200_ctx* c, mcb200_pipe_rate* out, int cap) {
     if (!c || !out || cap <= 0) return -fail(MCB200_ERR_INVALID, "bad microbench arguments");

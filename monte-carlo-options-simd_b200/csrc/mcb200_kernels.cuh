@@ -1,7 +1,7 @@
 // mcb200_kernels.cuh -- the fused GBM path + payoff kernels (sm_100a) and their fixed-order second pass.
 //
 // One kernel family replaces the reference's inner step and its six simulation cores:
-//   speed_update                    /root/reference/src/mc_simd.rs:9-21      -> quad_fast() / pair_fast() / pair_ref()
+//   speed_update                    /root/reference/src/mc_simd.rs:9-21      -> tri_fast() / pair_fast() / pair_ref()
 //   get_rand_uniform_f32x8          /root/reference/src/rand32x8.rs:5-21     -> uniforms built in pair_*()
 //   monte_carlo_pricing             src/mc_simd.rs:25-79                      -> simulate_kernel<*, PAYOFF_PRICE>
 //   monte_carlo_av_pricing          src/mc_simd.rs:82-149                     -> simulate_kernel<*, PAYOFF_AV>
@@ -73,6 +73,10 @@ struct SimArgs {
     // Small host batches (n_options <= kInlineMaxOptions) carry their six input columns in the launch parameters, so
     // the call needs no H2D copy at all.
     int use_inline;
+    unsigned one;            // the value 1, unknown to ptxas (tri_fast: carry adds stay on the FMA-heavy pipe)
+#ifdef MCB_TRACE
+    unsigned long long* trace;   // tools/kernel_timeline.py builds only: [n_warps][8] %globaltimer stamps (lane 0)
+#endif
     // Cross-GPU fused combine (trials-sharded operation without a collective): every GPU stores the finished moment
     // sums of an option into ITS row of an exchange buffer that lives on one GPU (peer memory over NVLink, mapped
     // through CUDA IPC) and bumps the option's cross-GPU arrival counter; the warp -- on whichever GPU -- that completes
@@ -221,13 +225,20 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 //   * work unit = a "round": 32 consecutive paths of one option, one path per lane.  The n_options * ceil(n_paths/32)
 //     rounds are dealt to the resident warps in contiguous, equal (+-1) ranges, so every SM sub-partition gets the same
 //     load whatever the batch shape (no CTA-level quantisation, no block barrier anywhere in the path loop);
-//   * the inner step is quad_fast(): three xoshiro256++ outputs feed four Box-Muller pairs (mcb200_pair.cuh);
+//   * the inner step is tri_fast(): two xoshiro256++ outputs feed three Box-Muller pairs (mcb200_pair.cuh);
 //   * every thread owns one generator stream for the whole launch (state loaded from / stored back to the pool, so
 //     consecutive launches continue the same substreams) and keeps its fp32 moment sums in registers;
 //   * when a warp leaves an option it reduces its sums (fp64, butterfly) into slot (warp + option) and bumps the
 //     option's arrival counter; the warp that completes the count sums the option's slots in warp order (fixed order:
 //     bit-reproducible, independent of which warp arrives last) and writes moments and/or final values and SEs.
 // Path data never leaves registers.
+#ifdef MCB_TRACE
+#define MCB_STAMP(k) do { if (a.trace && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); \
+                                                     a.trace[(size_t)w * 8 + (k)] = t_; } } while (0)
+#else
+#define MCB_STAMP(k) do { } while (0)
+#endif
+
 template <int STREAM, int PAYOFF, bool DUMP>
 __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) simulate_kernel(const __grid_constant__ SimArgs a) {
     constexpr int kEst = PayoffTraits<PAYOFF>::kEst;
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
     if (w >= a.n_warps) return;                              // tail of the last CTA when W is not a multiple of 8
     long long r = round_begin(w, R, W);
     const long long r_end = round_begin(w + 1, R, W);        // W <= R: never empty
+    MCB_STAMP(0);
 
     Xoshiro256 g;
     const size_t gtid = (size_t)w * 32 + lane;              // the generator stream belongs to the LOGICAL thread
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
     int k = (int)(r - (long long)o * a.rounds_per_option);   // round index inside option o
     bool enter = true;                                       // constants of option o not loaded yet
     bool fresh = true;                                       // next flush is the first of this (warp, option) segment
+    MCB_STAMP(1);
 
     while (r < r_end) {
         if (enter) {
@@ -290,11 +303,11 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                 }
                 float m = 0.0f;
                 if (STREAM == STREAM_FAST) {
-                    // four pairs per three generator outputs, then the 0..3 left-over pairs one output each
-                    const int quads = a.half_steps >> 2;
+                    // three pairs per two generator outputs, then the 0..2 left-over pairs one output each
+                    const int tris = a.half_steps / 3;
 #pragma unroll kQuadUnroll_
-                    for (int i = 0; i < quads; ++i) m = quad_fast(g, m);
-                    for (int i = quads << 2; i < a.half_steps; ++i) m = pair_fast(g, m);
+                    for (int i = 0; i < tris; ++i) m = tri_fast(g, m, a.one);
+                    for (int i = tris * 3; i < a.half_steps; ++i) m = pair_fast(g, m);
                 } else {
 #pragma unroll 2
                     for (int i = 0; i < a.half_steps; ++i) m = pair_ref(g, m);
@@ -304,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
             }
         }
         r += n_run;
+        MCB_STAMP(2);
         const bool option_done = (k == a.rounds_per_option);
         const bool segment_done = option_done || r == r_end;
 
@@ -407,10 +421,12 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                 }
             }
         }
+        MCB_STAMP(3);
         if (option_done) { ++o; k = 0; enter = true; fresh = true; }
         else { enter = false; fresh = false; }
     }
     if (STREAM == STREAM_FAST) xoshiro_store(g, a.pool + 4ull * gtid);
+    MCB_STAMP(4);
 }
 
 // Device-side completion wait of the cross-GPU fused combine: one thread spins on the epoch word of the exchange

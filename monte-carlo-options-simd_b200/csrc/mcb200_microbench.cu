@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 8) pair_kernel(uint32_t* sink, long 
     for (int i = 0; i < kPairIters; ++i) {
         if (GEN_ONLY) { uint32_t hi, lo; xoshiro_next_v<V>(g, hi, lo, one); mix ^= hi + lo; }
         else if (FMODE == 9) acc = quad_fast(g, acc);      // 4 pairs per call: the host scales the rate
+        else if (FMODE == 10) acc = tri_fast(g, acc, one);      // 3 pairs per call
         else acc = pair_fast_v<V, FMODE>(g, acc, two23, one);
         if (EXTRA == 1) { op_step<K_FFMA>(e0, y, z); op_step<K_FFMA>(e1, y, z); op_step<K_FFMA>(e0, y, z); op_step<K_FFMA>(e1, y, z); }
         if (EXTRA == 2) { op_step<K_LOP3>(e0, y, z); op_step<K_LOP3>(e1, y, z); }
@@ -159,7 +160,7 @@ static void run_pair(Bench& b, int ctas_per_sm = 8, int threads = kThreads) {
         smem = (size_t)(227 * 1024) / ctas_per_sm - 2048;          // k CTAs fit, k+1 do not
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { b.rc = -1; return; }
     }
-    timed(b, name, ctas_per_sm, (double)kPairIters * (FMODE == 9 ? 4 : 1), [&](int grid, uint32_t seed) {
+    timed(b, name, ctas_per_sm, (double)kPairIters * (FMODE == 9 ? 4 : FMODE == 10 ? 3 : 1), [&](int grid, uint32_t seed) {
         kern<<<grid, threads, smem, b.st>>>(b.d_sink, b.d_cycles, seed);
     }, threads);
 }
@@ -200,6 +201,11 @@ int run_microbench(cudaStream_t st, int sm_count, mcb200_pipe_rate* out, int cap
     run_pair<0, 9, false, 2, 0>(b, 4); run_pair<0, 9, false, 1, 0>(b, 4); run_pair<0, 9, false, 2, 0>(b, 8);   // quad_fast
     run_pair<0, 9, false, 4, 0>(b, 4); run_pair<0, 9, false, 2, 0>(b, 2); run_pair<0, 9, false, 2, 0>(b, 1, 256);
     run_pair<0, 9, false, 4, 0>(b, 1, 256); run_pair<0, 9, false, 2, 0>(b, 1, 128); run_pair<0, 9, false, 4, 0>(b, 1, 128);
+    // tri_fast (production): two outputs -> three pairs, 16-bit angle fields placed by PRMT
+    run_pair<0, 10, false, 1, 0>(b, 4); run_pair<0, 10, false, 2, 0>(b, 4); run_pair<0, 10, false, 3, 0>(b, 4);
+    run_pair<0, 10, false, 4, 0>(b, 4); run_pair<0, 10, false, 2, 0>(b, 8); run_pair<0, 10, false, 2, 0>(b, 3);
+    run_pair<0, 10, false, 2, 0>(b, 2); run_pair<0, 10, false, 2, 0>(b, 1, 256); run_pair<0, 10, false, 2, 0>(b, 1, 128);
+    run_pair<0, 10, false, 2, 1>(b, 4); run_pair<0, 10, false, 2, 2>(b, 4); run_pair<0, 10, false, 2, 3>(b, 4);
     // few warps per SM (named by resident warps per SM): how much of the pipe can 1 or 2 warps per sub-partition use?
     run_pair<0, 0, false, 8, 0>(b, 1, 256); run_pair<0, 0, false, 8, 0>(b, 1, 128); run_pair<0, 0, false, 4, 0>(b, 1, 128);
     run_pair<0, 0, false, 8, 0>(b, 1, 32);

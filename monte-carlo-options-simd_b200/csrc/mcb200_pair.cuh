@@ -2,8 +2,9 @@
 //
 // Replaces speed_update (/root/reference/src/mc_simd.rs:9-21) and the uniform adapter it calls
 // (/root/reference/src/rand32x8.rs:5-21).  Shared by the path kernels and the pipe microbenchmarks.
-//   quad_fast()  production: three generator outputs -> four pairs (the path loop of the kernels)
-//   pair_fast()  one generator output -> one pair (the 0..3 pairs left over when floor(steps/2) % 4 != 0)
+//   tri_fast()   production: two generator outputs -> three pairs (the path loop of the kernels)
+//   pair_fast()  one generator output -> one pair (the 0..2 pairs left over when floor(steps/2) % 3 != 0)
+//   quad_fast()  round-1 production step (three outputs -> four pairs), kept for the microbenchmark comparison
 //   pair_ref()   the reference's own consumption of the stream (parity mode)
 #pragma once
 #include <cstdint>
@@ -18,6 +19,7 @@ constexpr int kWarps = kThreads / 32;
 // costs nothing and buys register-resident accumulators.  Measured with tools/tune_unroll_occupancy.sh:
 //   price / antithetic kernels: 4 CTAs/SM (64 registers), 2 quads per iteration   (C2 0.82, C5R 0.97 of the roofline)
 //   Greeks kernel (20 moment registers): 3 CTAs/SM (85 registers), 4 quads per iteration   (C4 0.93 instead of 0.88)
+// (round-1 figures, quad_fast).  The unroll factors count tri_fast calls (3 pairs each) per loop iteration.
 // The MCB_* macros exist for that sweep only (MCB200_NVCC_FLAGS in build.py).
 #ifndef MCB_PRICE_CTAS
 #define MCB_PRICE_CTAS 4
@@ -133,6 +135,46 @@ __device__ __forceinline__ float quad_fast(Xoshiro256& g, float acc) {
     acc = bm_term(top23(w2), top23(w3), acc);
     acc = bm_term(top23(w4), top23(w5), acc);
     return bm_term(low_bytes23(w0, w2, w4), low_bytes23(w1, w3, w5), acc);
+}
+
+// Denser still: TWO 64-bit outputs -> THREE Box-Muller pairs (six time steps): 12.33 ALU-pipe instructions per pair
+// instead of 14.25, and the ALU pipe is what binds the kernel.
+//   words (w0, w1), (w2, w3) = (hi, lo) of the two outputs.  u1 of pairs A, B, C = top 23 bits of w0, w1, w2 (LEA.HI,
+//   the same (0,1] grid as before).  The ANGLES are 16-bit fields placed by one byte permute each: A = top half of w3,
+//   B = bottom half of w3, C = low bytes of w0 and w1 (one extra PRMT to gather them).  The permute takes the top byte
+//   0x3f from the bit pattern of pair A's [1,2) float, so the result is the float  0 01111111b mmmmmmm mmmmmmmm 0..0 :
+//   b = 1 -> 1 + m in [1,2), b = 0 -> (1 + m)/2 in [0.5,1), m on a 2^-15 grid.  With the angle scale 4 pi both
+//   halves are uniform over whole turns (2 turns + 2 m turns, or 1 + m turns): an equispaced angle grid of 2^15
+//   (b = 0) or 2^14 (b = 1) directions.  An equispaced grid of N directions reproduces every moment of the Gaussian
+//   up to order N - 1 exactly (the discrete average of exp(i j theta) vanishes unless N | j), so the angle needs far
+//   fewer bits than the radius; the radius keeps all 23.  No generator bit is used twice; 11 of 128 stay unused.
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
+    return r;
+}
+__device__ __forceinline__ float bm_term16(uint32_t b1, uint32_t ang_bits, float acc) {
+    const float u1 = 2.0f - __uint_as_float(b1);                    // b1: bit pattern of a float in [1,2)
+    const float rad = mufu_sqrt(fabsf(mufu_lg2(u1)));
+    const float ang = fmaf(__uint_as_float(ang_bits), 2.0f * kTwoPi, kQuarterPi);   // ang_bits: float in [0.5,2)
+    return fmaf(rad, mufu_sin(ang), acc);
+}
+// `one` is the value 1 delivered at run time (a kernel parameter): it keeps the carry halves of the generator's two
+// 64-bit adds on IMAD.X (FMA-heavy pipe); left alone, ptxas moves a quarter of them to IADD3.X on the ALU pipe.
+__device__ __forceinline__ float tri_fast(Xoshiro256& g, float acc, uint32_t one) {
+    uint32_t w0, w1, w2, w3;
+    xoshiro_next_v<XO_CARRY_MAD>(g, w0, w1, one);
+    xoshiro_next_v<XO_CARRY_MAD>(g, w2, w3, one);
+    const uint32_t fa = top23(w0), fb = top23(w1), fc = top23(w2);
+    // prmt<SEL>(x, fa): result bytes, most significant first = [fa.b3 (0x3f), x.bJ, x.bK, 0x00 (sign fill of 0x3f)]
+    const uint32_t aa = prmt<0x732F>(w3, fa);                        // w3.b3, w3.b2
+    const uint32_t ab = prmt<0x710F>(w3, fa);                        // w3.b1, w3.b0
+    const uint32_t t = prmt<0x0040>(w0, w1);                         // t.b1 = w1.b0, t.b0 = w0.b0
+    const uint32_t ac = prmt<0x710F>(t, fa);                         // w1.b0, w0.b0
+    acc = bm_term16(fa, aa, acc);
+    acc = bm_term16(fb, ab, acc);
+    return bm_term16(fc, ac, acc);
 }
 
 // Reference-stream pair update: consumes the generator exactly like rand32x8.rs:5-21 + mc_simd.rs:9-21

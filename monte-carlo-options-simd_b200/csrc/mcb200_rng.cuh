@@ -33,10 +33,18 @@ enum XoVariant : int {
     XO_ROT_WIDE = 4,    // r = rotl(a, 23) + s0  : IMAD.WIDE(a.lo, 2^23, s0) + IMAD(a.hi, 2^23, hi) + SHF.R + IMAD.WIDE(a.hi >> 9, one, .)
                         //                                                                        (was 2 SHF + IADD3 + IMAD.X)
     XO_ROT45_WIDE = 8,  // s3 = rotl(s3 ^ s1, 45): IMAD.WIDE + IMAD + IMAD.HI                              (was 2 SHF)
+    XO_CARRY_MAD = 16,  // high words of both 64-bit adds: madc.lo(x, one, y) = IMAD.X on the FMA-heavy pipe, always
+                        //   (ptxas otherwise turns some of them into IADD3.X on the binding ALU pipe); likewise the low
+                        //   word of t = s1 << 17 as IMAD(s1.lo, one << 17) (ptxas otherwise turns some into SHF)
 };
 
 __device__ __forceinline__ void add64(uint32_t al, uint32_t ah, uint32_t bl, uint32_t bh, uint32_t& rl, uint32_t& rh) {
     asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(rl), "=r"(rh) : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+}
+__device__ __forceinline__ void add64_mad(uint32_t al, uint32_t ah, uint32_t bl, uint32_t bh, uint32_t one, uint32_t& rl,
+                                          uint32_t& rh) {
+    asm("add.cc.u32 %0, %2, %4;\n\tmadc.lo.u32 %1, %3, %6, %5;"
+        : "=r"(rl), "=r"(rh) : "r"(al), "r"(ah), "r"(bl), "r"(bh), "r"(one));
 }
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
     uint64_t r;
@@ -70,6 +78,8 @@ __device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, 
     if (V & XO_ADD_WIDE) {
         unpack64(mad_wide(g.s3l, one, pack64(g.s0l, g.s0h)), al, ah);
         ah = mad_lo(g.s3h, one, ah);
+    } else if (V & XO_CARRY_MAD) {
+        add64_mad(g.s0l, g.s0h, g.s3l, g.s3h, one, al, ah);
     } else {
         add64(g.s0l, g.s0h, g.s3l, g.s3h, al, ah);
     }
@@ -83,13 +93,17 @@ __device__ __forceinline__ void xoshiro_next_v(Xoshiro256& g, uint32_t& out_hi, 
     } else {
         const uint32_t rh = __funnelshift_l(al, ah, 23);
         const uint32_t rl = __funnelshift_l(ah, al, 23);
-        add64(g.s0l, g.s0h, rl, rh, out_lo, out_hi);
+        if (V & XO_CARRY_MAD) add64_mad(rl, rh, g.s0l, g.s0h, one, out_lo, out_hi);
+        else add64(g.s0l, g.s0h, rl, rh, out_lo, out_hi);
     }
     // t = s1 << 17
     uint32_t tl, th;
     if (V & XO_T_WIDE) {
         unpack64(mad_wide(g.s1l, 1u << 17, 0ull), tl, th);
         th = mad_lo(g.s1h, 1u << 17, th);
+    } else if (V & XO_CARRY_MAD) {
+        tl = mad_lo(g.s1l, one << 17, 0u);                          // IMAD with a run-time 2^17: never an ALU-pipe SHF
+        th = __funnelshift_l(g.s1l, g.s1h, 17);
     } else {
         tl = g.s1l << 17;
         th = __funnelshift_l(g.s1l, g.s1h, 17);

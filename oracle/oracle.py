@@ -56,8 +56,8 @@ def lib():
         L.fast_model_stream_paths.argtypes = [_u64p, C.c_int, C.c_int, _fp]
         L.mc_scalar_price.restype = _f
         L.mc_scalar_price.argtypes = [_f] * 9 + [C.c_uint64, _dp, _dp]
-        L.fast_model_quad_terms.restype = None
-        L.fast_model_quad_terms.argtypes = [_u64p, C.c_int, _fp]
+        L.fast_model_tri_terms.restype = None
+        L.fast_model_tri_terms.argtypes = [_u64p, C.c_int, _fp, _fp]
         L.fast_model_constants.restype = None
         L.fast_model_constants.argtypes = [_f] * 5 + [_fp, _fp]
         L.fast_model_growth.restype = _f
@@ -152,12 +152,14 @@ def mc_scalar(spot, strike, vol, r, years, q, steps, num_trials, call_mult=1.0, 
     return dict(price=float(price), mean=mean.value, se=se.value)
 
 
-def fast_quad_terms(state, n):
-    """The four Box-Muller terms (pairs A, B, C, D) of n consecutive quads of the production convention: [n, 4]."""
+def fast_tri_terms(state, n):
+    """The three Box-Muller terms (pairs A, B, C) of n consecutive triples of the production convention and their
+    angles in turns modulo 1: ([n, 3], [n, 3], state after)."""
     st = np.array(state, dtype=np.uint64)
-    out = np.empty((n, 4), np.float32)
-    lib().fast_model_quad_terms(st.ctypes.data_as(_u64p), int(n), out.ctypes.data_as(_fp))
-    return out, st
+    out = np.empty((n, 3), np.float32)
+    turns = np.empty((n, 3), np.float32)
+    lib().fast_model_tri_terms(st.ctypes.data_as(_u64p), int(n), out.ctypes.data_as(_fp), turns.ctypes.data_as(_fp))
+    return out, turns, st
 
 
 def fast_constants(vol, r, q, years, steps):

@@ -148,30 +148,55 @@ def test_cpu_baseline_agrees_with_closed_form(oracle):
             assert abs(p - exact) < 0.35, (kind, s, p, exact)   # ~4 SE at 40000 trials (SE <= 0.09)
 
 
-def test_quad_convention_terms_are_iid_normal(oracle, xoshiro_kat):
-    """Production convention (three generator outputs -> four Box-Muller pairs): every term, including pair D that is
-    gathered from the left-over low bytes, has the law sqrt(-log2 u) sin(theta) ~ N(0, 1/(2 ln 2)), and the four terms
-    of a quad are uncorrelated in value and in square.  (The GPU reproduces this model path by path:
+def test_tri_convention_terms_are_iid_normal(oracle, xoshiro_kat):
+    """Production convention (two generator outputs -> three Box-Muller pairs, 23-bit radius uniforms, 16-bit angle
+    fields): every term has the law sqrt(-log2 u) sin(theta) ~ N(0, 1/(2 ln 2)), and the three terms of a triple are
+    uncorrelated in value and in square.  (The GPU reproduces this model path by path:
     tests/test_gpu_parity.py::test_production_stream_per_path_parity.)"""
     n = 400000
-    t, _ = oracle.fast_quad_terms([0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9, 0x94d049bb133111eb, 0x2545f4914f6cdd1d], n)
+    t, turns, _ = oracle.fast_tri_terms([0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9, 0x94d049bb133111eb, 0x2545f4914f6cdd1d], n)
     t = t.astype(np.float64)
     var = 1.0 / (2.0 * math.log(2.0))
-    for j in range(4):
+    for j in range(3):
         x = t[:, j]
         assert abs(x.mean()) < 4.0 * math.sqrt(var / n), j
         assert abs(x.var() / var - 1.0) < 4.0 * math.sqrt(2.0 / n), j
         assert abs((x ** 4).mean() / var ** 2 - 3.0) < 4.0 * math.sqrt(96.0 / n), j          # normal kurtosis
         assert abs((x ** 3).mean()) / var ** 1.5 < 4.0 * math.sqrt(15.0 / n), j              # no skew
+        assert abs((x ** 6).mean() / var ** 3 - 15.0) < 4.0 * math.sqrt(10170.0 / n), j      # sixth moment of a normal
         assert 4.0 < np.abs(x).max() / math.sqrt(var) <= 5.66       # 23-bit u1: the tail ends at sqrt(2*23*ln 2) = 5.65 sigma
     c = np.corrcoef(t.T)
     c2 = np.corrcoef((t ** 2).T)
-    off = ~np.eye(4, dtype=bool)
+    off = ~np.eye(3, dtype=bool)
     assert np.abs(c[off]).max() < 4.5 / math.sqrt(n) and np.abs(c2[off]).max() < 4.5 / math.sqrt(n)
-    # serial independence: term D of quad i against term A of quad i+1 (they share no generator output)
-    assert abs(np.corrcoef(t[:-1, 3], t[1:, 0])[0, 1]) < 4.5 / math.sqrt(n)
-    # sum of a quad = what a path accumulates: variance 4 * var
-    assert abs(t.sum(axis=1).var() / (4 * var) - 1.0) < 4.0 * math.sqrt(2.0 / n)
+    # serial independence: term C of triple i against term A of triple i+1 (they share no generator output)
+    assert abs(np.corrcoef(t[:-1, 2], t[1:, 0])[0, 1]) < 4.5 / math.sqrt(n)
+    # sum of a triple = what a path accumulates: variance 3 * var
+    assert abs(t.sum(axis=1).var() / (3 * var) - 1.0) < 4.0 * math.sqrt(2.0 / n)
+    # the angles: an equispaced grid of 2^15 directions (every second one only when the field's top bit is set),
+    # uniform over the circle; a Kolmogorov-Smirnov test against the uniform law and the first Fourier modes
+    for j in range(3):
+        k = turns[:, j].astype(np.float64) * 32768.0
+        assert np.array_equal(k, np.round(k)), j
+        u = np.sort(turns[:, j].astype(np.float64))
+        ks = np.abs(u - (np.arange(n) + 0.5) / n).max()
+        assert ks < 1.95 / math.sqrt(n), (j, ks)                   # 0.1 % critical value
+        for h in (1, 2, 3, 4, 8):
+            assert abs(np.exp(2j * math.pi * h * u).mean()) < 4.5 / math.sqrt(n), (j, h)
+    # distinct directions actually visited: far more than a test could tell from a continuum
+    assert len(np.unique(turns)) > 30000
+
+
+def test_equispaced_angle_grid_reproduces_gaussian_moments():
+    """Why 16-bit angles are enough: for theta on an equispaced grid of N directions (any offset) the average of
+    sin(theta)^p equals the continuous average for every p < N (the discrete mean of exp(i j theta) vanishes unless N
+    divides j), so r sin(theta) with an exact Rayleigh radius has exact Gaussian moments up to order N - 1."""
+    for n_dir in (64, 1 << 14, 1 << 15):
+        th = 2.0 * math.pi * (np.arange(n_dir) / n_dir) + math.pi / 4
+        for p in (2, 4, 6, 8, 12, 20):
+            exact = math.comb(p, p // 2) / 2.0 ** p                  # (1/2pi) int sin^p
+            assert abs((np.sin(th) ** p).mean() / exact - 1.0) < 1e-9, (n_dir, p)
+        assert abs(np.sin(th).mean()) < 1e-12 and abs((np.sin(th) ** 3).mean()) < 1e-12
 
 
 def test_scalar_mc_replays_mc_rs_tests(oracle, bs_cases):

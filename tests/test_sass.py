@@ -58,21 +58,25 @@ def test_all_kernel_variants_are_in_the_library(funcs):
         assert k in names
 
 
-@pytest.mark.parametrize("payoff,pairs_per_iter", [(0, 8), (1, 8), (2, 16)])
-def test_quad_loop_instruction_mix(funcs, payoff, pairs_per_iter):
-    """quad_fast loop of the production (STREAM_FAST) kernels: 3 MUFU and <= 24 instructions per Box-Muller pair, of
-    which <= 15 on the ALU pipe (LOP3 / SHF / IADD3 / LEA / PRMT: 6 LOP3 per pair = 8 per generator output), no
-    generic-address or local-memory traffic inside the loop."""
+@pytest.mark.parametrize("payoff,pairs_per_iter", [(0, 6), (1, 6), (2, 12)])
+def test_tri_loop_instruction_mix(funcs, payoff, pairs_per_iter):
+    """tri_fast loop of the production (STREAM_FAST) kernels: 3 MUFU and <= 22.25 instructions per Box-Muller pair, of
+    which <= 12.85 on the ALU pipe (LOP3 / SHF / IADD3 / LEA / PRMT + the loop counter); every carry add and every
+    low-word shift of the generator on the FMA-heavy pipe (IMAD.X / IMAD); no memory traffic inside the loop."""
     name = next(n for n in funcs if "simulate_kernelILi0ELi%dELb0E" % payoff in n)
     mufu, loop = _densest_mufu_loop(funcs[name])
     assert mufu == 3 * pairs_per_iter                               # LG2 + SQRT + SIN per pair, nothing else on the XU pipe
     ops = [x[1].split(".")[0] for x in loop]
+    full = [x[1] for x in loop]
+    outputs = 2 * pairs_per_iter // 3                               # generator outputs per iteration
     per_pair = len(loop) / pairs_per_iter
     alu = sum(o in ("LOP3", "SHF", "IADD3", "LEA", "PRMT", "VIADD", "ISETP", "IADD", "SEL", "MOV") for o in ops) / pairs_per_iter
-    assert per_pair <= 24.25, per_pair
-    assert alu <= 15.0, alu
-    assert ops.count("PRMT") == pairs_per_iter                      # pair D of every quad: 2 fields x 2 byte gathers
-    assert ops.count("LOP3") == 6 * pairs_per_iter                  # 8 per generator output, 0.75 outputs per pair
+    assert per_pair <= 22.25, per_pair
+    assert alu <= 12.85, alu
+    assert ops.count("LOP3") == 8 * outputs and ops.count("SHF") == 5 * outputs
+    assert ops.count("IADD3") == 2 * outputs                        # low words of the two 64-bit adds ...
+    assert sum(f.startswith("IMAD.X") for f in full) == 2 * outputs  # ... their carry halves stay off the ALU pipe
+    assert ops.count("PRMT") == 4 * pairs_per_iter // 3 and ops.count("LEA") == pairs_per_iter
     assert not any(o in ("LDL", "STL", "LD", "ST", "LDG", "STG", "LDS", "STS") for o in ops)
     kinds = {x[1] for x in loop if x[1].startswith("MUFU")}
     assert kinds == {"MUFU.LG2", "MUFU.SQRT", "MUFU.SIN"}
