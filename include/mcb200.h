@@ -78,6 +78,38 @@ typedef struct {
 int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan *out);
 int mcb200_plan_warp_range(const mcb200_plan *plan, int warp, int64_t *first_round, int64_t *end_round);
 
+/* ------------------------------------------------------------------ several GPUs -------------------------------- */
+/* The reference parallelises INSIDE a call: chunks of 8 paths fan out over a thread pool (src/mc_simd.rs:49-51) and
+ * are reduced (src/mc_simd.rs:71-74).  The node-scale equivalent is a multi-device context: one process, one per-device
+ * context + host worker thread + stream per listed device (a device may be listed more than once), device i on
+ * substream block first_substream_block + i.  The HOST-BUFFER entry points (mcb200_price_batch, mcb200_greeks_batch,
+ * mcb200_bs_batch and the twelve drop-ins through MCB200_DEVICES=0,1,..) accept it and split every batch by the
+ * policy of mcb200_shard_query; the *_device, xgpu and inspection entry points are per device (mcb200_ctx_child).
+ * Results are a function of (seed, first block, device COUNT, call sequence): reproducible bit for bit, and the
+ * trials-minor sum runs in device order on the host.  Destroy with mcb200_ctx_destroy. */
+int mcb200_ctx_create_multi(mcb200_ctx **ctx, const int *devices, int n_devices, uint64_t seed,
+                            uint32_t first_substream_block);
+int mcb200_ctx_device_count(mcb200_ctx *ctx);                       /* 1 for a plain context */
+int mcb200_ctx_child(mcb200_ctx *ctx, int i, mcb200_ctx **child);  /* borrowed per-device context of a multi-device one */
+
+/* How one batch is split over n_shards GPUs -- the same policy for the multi-device context (shard = device index) and
+ * for one-process-per-GPU operation (shard = rank).  Pure host logic.
+ *   MCB200_SHARD_SINGLE   the batch does not fill one GPU (or n_shards == 1): shard 0 runs all of it;
+ *   MCB200_SHARD_OPTIONS  n_options >= 16 * n_shards: shard s owns options [s*n/S, (s+1)*n/S), no exchange step;
+ *   MCB200_SHARD_TRIALS   otherwise: shard s simulates chunks [s*C/S, (s+1)*C/S) of the C = floor(num_trials/8) 8-path
+ *                         chunks of EVERY option; per-option fp64 moment sums are added in shard order and finalised
+ *                         once with total_paths and the caller's num_trials (the divisor of mc_simd.rs:77). */
+enum { MCB200_SHARD_SINGLE = 0, MCB200_SHARD_OPTIONS = 1, MCB200_SHARD_TRIALS = 2 };
+typedef struct {
+    int mode, n_shards, shard;
+    int active;                  /* 0: this shard has nothing to do */
+    int option_begin, option_end;
+    float num_trials_local;      /* num_trials to pass to this shard's launch */
+    double total_paths;          /* 8 * floor(num_trials / 8): paths of the whole sample per option */
+} mcb200_shard;
+int mcb200_shard_query(int n_options, float steps, float num_trials, int n_shards, int shard, int grid_slots,
+                       mcb200_shard *out);
+
 /* ------------------------------------------------------------------ batched entry points (new) ----------------- */
 /* Host buffers: the call returns when the outputs are valid.  Inputs reach the device through a pinned staging copy
  * (batches of <= 128 options ride in the launch parameters instead); outputs come back through a D2H copy (batches of

@@ -13,4 +13,4 @@ reference's interface and the ctypes plumbing.  No CPU fallback.
 from . import _native, mc_simd, sharding  # noqa: F401
 from ._native import GREEK_NAMES, LIB_PATH, Mcb200Error  # noqa: F401
 from .build import build  # noqa: F401
-from .context import Context, plan_query, plan_warp_range  # noqa: F401
+from .context import Context, plan_query, plan_warp_range, shard_query  # noqa: F401

@@ -38,6 +38,15 @@ class Plan(C.Structure):
                 ("path_steps", C.c_double)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("mode", C.c_int), ("n_shards", C.c_int), ("shard", C.c_int), ("active", C.c_int),
+                ("option_begin", C.c_int), ("option_end", C.c_int), ("num_trials_local", C.c_float),
+                ("total_paths", C.c_double)]
+
+
+SHARD_MODES = ("single", "options", "trials")
+
+
 class Bumps(C.Structure):
     _fields_ = [("delta_spot", _f), ("delta_volatility", _f), ("delta_risk_free_rate", _f),
                 ("delta_years_to_expiry", _f)]
@@ -103,6 +112,18 @@ def lib():
     L.mcb200_xgpu_create.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     L.mcb200_xgpu_open.restype = C.c_int
     L.mcb200_xgpu_open.argtypes = [_vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int]
+    L.mcb200_xgpu_attach.restype = C.c_int
+    L.mcb200_xgpu_attach.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int]
+    L.mcb200_xgpu_set_timeout.restype = C.c_int
+    L.mcb200_xgpu_set_timeout.argtypes = [_vp, C.c_double]
+    L.mcb200_ctx_create_multi.restype = C.c_int
+    L.mcb200_ctx_create_multi.argtypes = [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint32]
+    L.mcb200_ctx_device_count.restype = C.c_int
+    L.mcb200_ctx_device_count.argtypes = [_vp]
+    L.mcb200_ctx_child.restype = C.c_int
+    L.mcb200_ctx_child.argtypes = [_vp, C.c_int, C.POINTER(_vp)]
+    L.mcb200_shard_query.restype = C.c_int
+    L.mcb200_shard_query.argtypes = [C.c_int, _f, _f, C.c_int, C.c_int, C.c_int, C.POINTER(Shard)]
     L.mcb200_xgpu_close.restype = C.c_int
     L.mcb200_xgpu_close.argtypes = [_vp]
     L.mcb200_price_xgpu_device.restype = C.c_int

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, os.environ.get("MCB200_LIB_NAME", "libmcb200.so"))     # alternate name: tuning builds only
-SOURCES = ["mcb200_api.cu", "mcb200_microbench.cu", "mcb200_plan.cpp"]
+SOURCES = ["mcb200_api.cu", "mcb200_multi.cu", "mcb200_microbench.cu", "mcb200_plan.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"   # the image's CC/CXX wrappers lack libgomp etc.
 

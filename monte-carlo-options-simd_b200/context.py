@@ -13,15 +13,36 @@ class Context:
     GPUs / processes never share draws.
     """
 
-    def __init__(self, device=0, seed=0x5EED5EED5EED5EED, substream_block=0):
+    def __init__(self, device=0, seed=0x5EED5EED5EED5EED, substream_block=0, devices=None, _borrowed=None):
+        """devices=[0, 1, ...] creates a multi-device context (mcb200_ctx_create_multi): the host-buffer methods
+        (price_batch, greeks_batch, bs_batch, prepare_*) then split every batch over those GPUs; device i draws from
+        substream block substream_block + i."""
         self._h = C.c_void_p()
-        N.check(N.lib().mcb200_ctx_create(C.byref(self._h), int(device), int(seed) & (2 ** 64 - 1),
-                                          int(substream_block)))
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+        elif devices is not None:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            N.check(N.lib().mcb200_ctx_create_multi(C.byref(self._h), ids, len(devices), int(seed) & (2 ** 64 - 1),
+                                                    int(substream_block)))
+        else:
+            N.check(N.lib().mcb200_ctx_create(C.byref(self._h), int(device), int(seed) & (2 ** 64 - 1),
+                                              int(substream_block)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            N.lib().mcb200_ctx_destroy(self._h)
+            if self._owned:
+                N.lib().mcb200_ctx_destroy(self._h)
             self._h = C.c_void_p()
+
+    def device_count(self):
+        return int(N.lib().mcb200_ctx_device_count(self._h))
+
+    def child(self, i):
+        """Borrowed per-device context of a multi-device context (valid while the parent lives)."""
+        h = C.c_void_p()
+        N.check(N.lib().mcb200_ctx_child(self._h, int(i), C.byref(h)))
+        return Context(_borrowed=h.value)
 
     __del__ = close
 
@@ -243,6 +264,13 @@ class Context:
         h = (C.c_uint8 * N.IPC_HANDLE_BYTES).from_buffer_copy(bytes(handle))
         N.check(N.lib().mcb200_xgpu_open(self._h, h, int(n_max), int(world), 1 if greeks else 0))
 
+    def xgpu_attach(self, owner, n_max, world, greeks=False):
+        """Same-process ranks: share `owner`'s exchange buffer through plain peer access (no IPC handle)."""
+        N.check(N.lib().mcb200_xgpu_attach(self._h, owner._h, int(n_max), int(world), 1 if greeks else 0))
+
+    def xgpu_set_timeout(self, seconds):
+        N.check(N.lib().mcb200_xgpu_set_timeout(self._h, float(seconds)))
+
     def xgpu_close(self):
         N.check(N.lib().mcb200_xgpu_close(self._h))
 
@@ -292,6 +320,19 @@ def plan_query(n_options, steps, num_trials, grid_slots):
     if st != 0:
         raise N.Mcb200Error(st, "invalid plan request")
     return {k: getattr(p, k) for k, _ in N.Plan._fields_}
+
+
+def shard_query(n_options, steps, num_trials, n_shards, shard, grid_slots):
+    """How a batch is split over n_shards GPUs (mcb200_shard_query; pure host logic): dict with mode in
+    ('single', 'options', 'trials'), active, option_begin, option_end, num_trials_local, total_paths."""
+    s = N.Shard()
+    st = N.lib().mcb200_shard_query(int(n_options), float(steps), float(num_trials), int(n_shards), int(shard),
+                                    int(grid_slots), C.byref(s))
+    if st != 0:
+        raise N.Mcb200Error(st, "invalid shard request")
+    d = {k: getattr(s, k) for k, _ in N.Shard._fields_}
+    d["mode"] = N.SHARD_MODES[d["mode"]]
+    return d
 
 
 def plan_warp_range(plan, warp):

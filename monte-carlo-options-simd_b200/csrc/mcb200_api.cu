@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <cuda_runtime.h>
@@ -18,6 +19,7 @@
 #include "../../include/xoshiro256_jump_tables.h"
 #include "mcb200_kernels.cuh"
 #include "mcb200_plan.h"
+#include "mcb200_internal.h"
 
 namespace mcb200 {
 
@@ -87,18 +89,50 @@ struct mcb200_ctx {
     float* h_stage = nullptr; float* d_stage = nullptr; size_t stage_cap = 0;   // floats (pinned+mapped host / device)
     float* h_stage_dev = nullptr;  // device-side address of h_stage: small batches write their results straight to it
     // cross-GPU exchange buffer (trials-sharded fused combine): owned (cudaMalloc) or opened through CUDA IPC
-    void* xg_base = nullptr; bool xg_owner = false; int xg_world = 0, xg_n_max = 0, xg_n_acc = 0;
+    // (same-process ranks attach to the owner's allocation directly: plain peer access, mcb200_xgpu_attach)
+    void* xg_base = nullptr; bool xg_owner = false; bool xg_attached = false; int xg_world = 0, xg_n_max = 0, xg_n_acc = 0;
     unsigned xg_epoch = 0;        // rounds launched through the exchange buffer (all ranks call in lockstep)
+    bool xg_pending = false;      // a round was launched and its results not fetched yet: launch and results alternate
+    unsigned long long xg_timeout_ns = 120ull * 1000 * 1000 * 1000;   // device-side wait for the other ranks
     int* xg_status = nullptr;     // device word written by xgpu_wait_kernel
     cudaEvent_t xg_event = nullptr;   // recorded behind the latest xgpu launch (it may sit on a caller stream)
     uint64_t launches = 0;
+    // Launch ordering.  Pool, slots and arrival counters are one set per context, so two launches of one context must
+    // never overlap on the device: every launch records order_ev behind itself, and a launch that arrives on a
+    // different stream than its predecessor first waits for that event (cudaStreamWaitEvent, device side only).
+    cudaEvent_t order_ev = nullptr; cudaStream_t order_stream = nullptr; bool order_valid = false;
 #ifdef MCB_TRACE
     unsigned long long* trace = nullptr;    // device buffer of the timeline build (tools/kernel_timeline.py)
 #endif
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mcb200::MultiRuntime* multi = nullptr;   // non-null: this is the parent of a multi-device context (mcb200_multi.cu)
     std::mutex mu;
 };
+
+namespace mcb200 {
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+MultiRuntime* ctx_multi(mcb200_ctx* c) { return c ? c->multi : nullptr; }
+mcb200_ctx* ctx_new_parent(MultiRuntime* m, int device0, uint64_t seed, uint32_t first_block) {
+    mcb200_ctx* c = new (std::nothrow) mcb200_ctx();
+    if (c) { c->multi = m; c->device = device0; c->seed = seed; c->block = first_block; }
+    return c;
+}
+}  // namespace mcb200
+
+// Device pointers and streams belong to ONE device: the *_device, xgpu and inspection entry points refuse a parent.
+#define SINGLE_DEVICE_ONLY(c, what)                                                                        \
+    do {                                                                                                   \
+        if ((c) && (c)->multi)                                                                             \
+            return fail(MCB200_ERR_INVALID, what ": not available on a multi-device context (use the host-buffer " \
+                        "entry points, or mcb200_ctx_child for one device)");                             \
+    } while (0)
 
 static int ensure(double** p, size_t* cap, size_t need) {
     if (*cap >= need) return MCB200_OK;
@@ -139,7 +173,9 @@ static int seed_pool(mcb200_ctx* c) {
     uint64_t x = c->seed;
     HostXo base;
     for (int k = 0; k < 4; ++k) base.s[k] = h_splitmix(x);
-    for (uint32_t b = 0; b < c->block; ++b) h_apply_poly(base, XOSHIRO256_LONG_JUMP);
+    // long_jump^block in O(log block): one polynomial x^(2^(192+k)) per set bit of the block index
+    for (int k = 0; k < XOSHIRO256_LONG_JUMP_POW2_COUNT; ++k)
+        if ((c->block >> k) & 1u) h_apply_poly(base, XOSHIRO256_LONG_JUMP_POW2[k]);
     const ulonglong4 bs = make_ulonglong4(base.s[0], base.s[1], base.s[2], base.s[3]);
     const int threads = 128;
     const int blocks = (int)((c->pool_threads + threads - 1) / threads);
@@ -148,6 +184,18 @@ static int seed_pool(mcb200_ctx* c) {
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    return MCB200_OK;
+}
+
+// Called with the context mutex held, before / after enqueuing work that touches the context's shared device state.
+static int order_before(mcb200_ctx* c, cudaStream_t st) {
+    if (c->order_valid && c->order_stream != st) CU(cudaStreamWaitEvent(st, c->order_ev, 0));
+    return MCB200_OK;
+}
+static int order_after(mcb200_ctx* c, cudaStream_t st) {
+    if (!c->order_ev) CU(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->order_ev, st));
+    c->order_stream = st; c->order_valid = true;
     return MCB200_OK;
 }
 
@@ -205,10 +253,12 @@ extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, ui
 
 extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (!c) return;
+    if (c->multi) { multi_destroy(c->multi); delete c; return; }
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->order_ev) cudaEventDestroy(c->order_ev);
     if (c->pool) cudaFree(c->pool);
     if (c->d_jump) cudaFree(c->d_jump);
     if (c->slots) cudaFree(c->slots);
@@ -216,7 +266,7 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (c->moments) cudaFree(c->moments);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
-    if (c->xg_base) { if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base); }
+    if (c->xg_base) { if (c->xg_owner) cudaFree(c->xg_base); else if (!c->xg_attached) cudaIpcCloseMemHandle(c->xg_base); }
     if (c->xg_status) cudaFree(c->xg_status);
     if (c->xg_event) cudaEventDestroy(c->xg_event);
     delete c;
@@ -224,6 +274,7 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
 
 extern "C" int mcb200_ctx_set_seed(mcb200_ctx* c, uint64_t seed, uint32_t substream_block) {
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    if (c->multi) { c->seed = seed; c->block = substream_block; return multi_set_seed(c->multi, seed, substream_block); }
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->seed = seed; c->block = substream_block;
@@ -234,6 +285,11 @@ extern "C" const char* mcb200_last_error(void) { return g_err; }
 
 extern "C" int mcb200_ctx_info(mcb200_ctx* c, mcb200_info* out) {
     if (!c || !out) return fail(MCB200_ERR_INVALID, "null argument");
+    if (c->multi) {                          // the first device's figures; launches summed over all devices
+        int rc = mcb200_ctx_info(multi_child(c->multi, 0), out);
+        if (rc == MCB200_OK) { out->kernel_launches = multi_launches(c->multi); out->seed = c->seed; out->substream_block = c->block; }
+        return rc;
+    }
     out->device = c->device; out->sm_count = c->sm_count; out->ctas_per_sm = c->ctas_per_sm;
     out->threads_per_cta = kThreads; out->grid_slots = c->grid_slots; out->grid_slots_greeks = c->grid_slots_greeks;
     out->pool_threads = c->pool_threads;
@@ -318,11 +374,13 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
             if ((rc = ensure(&c->moments, &c->moments_cap, (size_t)rq.n * n_acc))) return rc;
             mo = c->moments;
         }
+        if ((rc = order_before(c, st))) return rc;
         CU(cudaMemsetAsync(mo, 0, sizeof(double) * (size_t)rq.n * n_acc, st));
         if (finalize)
-            return run_finalize(c, rq.n, n_est, mo, 0.0, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out,
-                                out_se, st);
-        return MCB200_OK;
+            rc = run_finalize(c, rq.n, n_est, mo, 0.0, (double)rq.num_trials, rq.opt.rate, rq.opt.years, rq.bumps, out,
+                              out_se, st);
+        if (rc) return rc;
+        return order_after(c, st);
     }
     if ((rc = ensure(&c->slots, &c->slots_cap, ((size_t)pl.warps + (size_t)rq.n) * n_acc))) return rc;
     if ((rc = ensure_arrivals(c, (size_t)rq.n))) return rc;
@@ -338,7 +396,7 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
 #endif
     if (rq.xg) {
         XgLayout L = xg_layout(c);
-        a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_ctl = L.ctl; a.xg_epoch = c->xg_epoch;
+        a.xg_slots = L.slots; a.xg_arrivals = L.arrivals; a.xg_ctl = L.ctl; a.xg_epoch = c->xg_epoch + 1;
         a.xg_rank = rq.xg_rank; a.xg_world = c->xg_world;
         a.xg_n_max = c->xg_n_max;
         a.fin.n_paths = rq.xg_total_paths; a.fin.num_trials = rq.xg_total_trials;
@@ -348,6 +406,7 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
         for (int k = 0; k < 6; ++k) std::memcpy(a.inline_opt[k], rq.inline_cols[k], sizeof(float) * rq.n);
     }
     const int key = rq.stream_mode * 100 + rq.payoff * 10 + (rq.dump ? 1 : 0);
+    if ((rc = order_before(c, st))) return rc;
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     switch (key) {
         case 0:   launch_sim<STREAM_FAST, PAYOFF_PRICE, false>(a, pl.grid, st); break;
@@ -365,11 +424,12 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) { CU(cudaEventRecord(c->ev1, st)); c->timed_once = true; }
-    return MCB200_OK;
+    return order_after(c, st);
 }
 
 static int check_common(mcb200_ctx* c, int n, const float* const* arrays, int n_arrays) {
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
+    SINGLE_DEVICE_ONLY(c, "device-pointer entry point");
     if (n < 0) return fail(MCB200_ERR_INVALID, "n = %d < 0", n);
     if (n > 0)
         for (int i = 0; i < n_arrays; ++i)
@@ -491,13 +551,15 @@ static_assert(sizeof(cudaIpcMemHandle_t) == MCB200_IPC_HANDLE_BYTES, "IPC handle
 static int xg_release(mcb200_ctx* c) {
     if (c->xg_base) {
         cudaStreamSynchronize(c->stream);
-        if (c->xg_owner) cudaFree(c->xg_base); else cudaIpcCloseMemHandle(c->xg_base);
+        if (c->xg_owner) cudaFree(c->xg_base); else if (!c->xg_attached) cudaIpcCloseMemHandle(c->xg_base);
     }
-    c->xg_base = nullptr; c->xg_owner = false; c->xg_world = c->xg_n_max = c->xg_n_acc = 0; c->xg_epoch = 0;
+    c->xg_base = nullptr; c->xg_owner = false; c->xg_attached = false; c->xg_world = c->xg_n_max = c->xg_n_acc = 0;
+    c->xg_epoch = 0; c->xg_pending = false;
     return MCB200_OK;
 }
 
 extern "C" int mcb200_xgpu_create(mcb200_ctx* c, int n_max, int world, int greeks, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES]) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_create");
     if (!c || !handle_out || n_max <= 0 || world <= 0) return fail(MCB200_ERR_INVALID, "bad xgpu_create arguments");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -514,6 +576,7 @@ extern "C" int mcb200_xgpu_create(mcb200_ctx* c, int n_max, int world, int greek
 }
 
 extern "C" int mcb200_xgpu_open(mcb200_ctx* c, const uint8_t handle[MCB200_IPC_HANDLE_BYTES], int n_max, int world, int greeks) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_open");
     if (!c || !handle || n_max <= 0 || world <= 0) return fail(MCB200_ERR_INVALID, "bad xgpu_open arguments");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -525,7 +588,49 @@ extern "C" int mcb200_xgpu_open(mcb200_ctx* c, const uint8_t handle[MCB200_IPC_H
     return MCB200_OK;
 }
 
+// Same-process variant of mcb200_xgpu_open: several contexts of ONE process (one per GPU, or several on one GPU) share
+// the owner's allocation through plain peer access -- no IPC handle.  The owner must outlive the attached contexts'
+// use of the buffer.
+extern "C" int mcb200_xgpu_attach(mcb200_ctx* c, mcb200_ctx* owner, int n_max, int world, int greeks) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_attach");
+    if (!c || !owner || c == owner || n_max <= 0 || world <= 0) return fail(MCB200_ERR_INVALID, "bad xgpu_attach arguments");
+    const int n_acc = 2 * (greeks ? EST_COUNT_GREEKS : EST_COUNT_PRICE);
+    void* base = nullptr;
+    unsigned epoch = 0;
+    {
+        std::lock_guard<std::mutex> lk(owner->mu);
+        if (!owner->xg_base || !owner->xg_owner || owner->xg_n_max != n_max || owner->xg_world != world || owner->xg_n_acc != n_acc)
+            return fail(MCB200_ERR_INVALID, "xgpu_attach: the owner holds no exchange buffer of this shape (n_max=%d world=%d)", n_max, world);
+        if (owner->xg_pending) return fail(MCB200_ERR_INVALID, "xgpu_attach: the owner has a round pending");
+        base = owner->xg_base;
+        epoch = owner->xg_epoch;           // join the owner's round count (attach between rounds, on every rank alike)
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    xg_release(c);
+    if (c->device != owner->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, c->device, owner->device));
+        if (!can) return fail(MCB200_ERR_CUDA, "xgpu_attach: device %d cannot access device %d", c->device, owner->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(MCB200_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    }
+    c->xg_base = base; c->xg_owner = false; c->xg_attached = true; c->xg_world = world; c->xg_n_max = n_max; c->xg_n_acc = n_acc;
+    c->xg_epoch = epoch;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_xgpu_set_timeout(mcb200_ctx* c, double seconds) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_set_timeout");
+    if (!c || !(seconds > 0.0) || seconds > 86400.0) return fail(MCB200_ERR_INVALID, "bad xgpu timeout");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->xg_timeout_ns = (unsigned long long)(seconds * 1e9);
+    return MCB200_OK;
+}
+
 extern "C" int mcb200_xgpu_close(mcb200_ctx* c) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_close");
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -546,6 +651,8 @@ extern "C" int mcb200_price_xgpu_device(mcb200_ctx* c, int n, const float* spot,
     if (!c->xg_base) return fail(MCB200_ERR_INVALID, "no exchange buffer: call mcb200_xgpu_create / mcb200_xgpu_open first");
     if (n > c->xg_n_max || rank < 0 || rank >= c->xg_world || c->xg_n_acc != 2 * EST_COUNT_PRICE)
         return fail(MCB200_ERR_INVALID, "xgpu: n=%d (max %d), rank=%d (world %d)", n, c->xg_n_max, rank, c->xg_world);
+    if (c->xg_pending)
+        return fail(MCB200_ERR_INVALID, "xgpu: round %u is still pending -- fetch it with mcb200_xgpu_results before launching the next", c->xg_epoch);
     mcb200_plan pl;
     if (make_plan(n, steps, num_trials_local, c->grid_slots, &pl) != MCB200_OK || pl.n_paths == 0)
         return fail(MCB200_ERR_INVALID, "xgpu: every rank must simulate at least 8 trials (steps=%g trials=%g)", steps, num_trials_local);
@@ -553,13 +660,13 @@ extern "C" int mcb200_price_xgpu_device(mcb200_ctx* c, int n, const float* spot,
     rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials_local;
     rq.payoff = (flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE;
     rq.xg = true; rq.xg_rank = rank; rq.xg_total_paths = total_paths; rq.xg_total_trials = total_num_trials;
-    ++c->xg_epoch;                        // every rank launches the same rounds in the same order
     const XgLayout L = xg_layout(c);
     float* out[2] = {L.results, L.results + c->xg_n_max};
     float* se[2] = {L.results + 2 * (size_t)c->xg_n_max, L.results + 3 * (size_t)c->xg_n_max};
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
-    rc = run_sim(c, rq, nullptr, true, out, se, st, nullptr);
+    rc = run_sim(c, rq, nullptr, true, out, se, st, nullptr);      // launches round xg_epoch + 1
     if (rc) return rc;
+    ++c->xg_epoch; c->xg_pending = true;  // counted only once the launch is in the stream: ranks stay in step on errors
     if (!c->xg_event) CU(cudaEventCreateWithFlags(&c->xg_event, cudaEventDisableTiming));
     CU(cudaEventRecord(c->xg_event, st));
     return MCB200_OK;
@@ -579,14 +686,15 @@ extern "C" int mcb200_greeks_xgpu_device(mcb200_ctx* c, int n, const float* spot
     if (n > c->xg_n_max || rank < 0 || rank >= c->xg_world || c->xg_n_acc != 2 * EST_COUNT_GREEKS)
         return fail(MCB200_ERR_INVALID, "xgpu (greeks): n=%d (max %d), rank=%d (world %d), buffer created for %d sums",
                     n, c->xg_n_max, rank, c->xg_world, c->xg_n_acc);
+    if (c->xg_pending)
+        return fail(MCB200_ERR_INVALID, "xgpu: round %u is still pending -- fetch it with mcb200_xgpu_results_greeks before launching the next", c->xg_epoch);
     mcb200_plan pl;
-    if (make_plan(n, steps, num_trials_local, c->grid_slots, &pl) != MCB200_OK || pl.n_paths == 0)
+    if (make_plan(n, steps, num_trials_local, c->grid_slots_greeks, &pl) != MCB200_OK || pl.n_paths == 0)
         return fail(MCB200_ERR_INVALID, "xgpu: every rank must simulate at least 8 trials (steps=%g trials=%g)", steps, num_trials_local);
     Request rq;
     rq.n = n; rq.opt = OptionArrays{spot, strike, vol, rate, years, div}; rq.steps = steps; rq.num_trials = num_trials_local;
     rq.payoff = PAYOFF_GREEKS; rq.bumps = to_bumps(bumps);
     rq.xg = true; rq.xg_rank = rank; rq.xg_total_paths = total_paths; rq.xg_total_trials = total_num_trials;
-    ++c->xg_epoch;
     const XgLayout L = xg_layout(c);
     float* out[EST_COUNT_GREEKS]; float* se[EST_COUNT_GREEKS];
     for (int e = 0; e < EST_COUNT_GREEKS; ++e) {
@@ -596,6 +704,7 @@ extern "C" int mcb200_greeks_xgpu_device(mcb200_ctx* c, int n, const float* spot
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     rc = run_sim(c, rq, nullptr, true, out, se, st, nullptr);
     if (rc) return rc;
+    ++c->xg_epoch; c->xg_pending = true;
     if (!c->xg_event) CU(cudaEventCreateWithFlags(&c->xg_event, cudaEventDisableTiming));
     CU(cudaEventRecord(c->xg_event, st));
     return MCB200_OK;
@@ -606,7 +715,7 @@ extern "C" int mcb200_greeks_xgpu_device(mcb200_ctx* c, int n, const float* spot
 static int xg_fetch(mcb200_ctx* c, int n, int n_est, float* const* out, float* const* out_se) {
     if (!c->xg_base || n < 0 || n > c->xg_n_max || c->xg_n_acc != 2 * n_est)
         return fail(MCB200_ERR_INVALID, "xgpu_results: no matching exchange buffer or bad n");
-    if (c->xg_epoch == 0) return fail(MCB200_ERR_INVALID, "xgpu_results: nothing was launched through the exchange buffer");
+    if (!c->xg_pending) return fail(MCB200_ERR_INVALID, "xgpu_results: no round is pending (launch and results alternate)");
     const XgLayout L = xg_layout(c);
     if (!c->xg_status) CU(cudaMalloc((void**)&c->xg_status, sizeof(int)));
     const size_t out_f = (size_t)c->xg_n_acc * c->xg_n_max;
@@ -615,7 +724,7 @@ static int xg_fetch(mcb200_ctx* c, int n, int n_est, float* const* out, float* c
     cudaStream_t st = c->stream;
     // the wait kernel must not share the GPU with this rank's own path kernel (it would take a CTA slot from it)
     if (c->xg_event) CU(cudaStreamWaitEvent(st, c->xg_event, 0));
-    xgpu_wait_kernel<<<1, 1, 0, st>>>(L.ctl, c->xg_epoch, 20ull * 1000 * 1000 * 1000, c->xg_status);
+    xgpu_wait_kernel<<<1, 1, 0, st>>>(L.ctl, c->xg_epoch, c->xg_timeout_ns, c->xg_status);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_stage, L.results, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st));
@@ -623,7 +732,9 @@ static int xg_fetch(mcb200_ctx* c, int n, int n_est, float* const* out, float* c
     CU(cudaStreamSynchronize(st));
     int ok = 0;
     std::memcpy(&ok, c->h_stage + out_f, sizeof(int));
-    if (!ok) return fail(MCB200_ERR_CUDA, "xgpu_results: round %u was not completed by all ranks within 20 s", c->xg_epoch);
+    c->xg_pending = false;
+    if (!ok) return fail(MCB200_ERR_CUDA, "xgpu_results: round %u was not completed by all ranks within %.0f s", c->xg_epoch,
+                         (double)c->xg_timeout_ns * 1e-9);
     for (int e = 0; e < n_est; ++e) {
         if (out && out[e] && n > 0) std::memcpy(out[e], c->h_stage + (size_t)e * c->xg_n_max, sizeof(float) * n);
         if (out_se && out_se[e] && n > 0) std::memcpy(out_se[e], c->h_stage + (size_t)(n_est + e) * c->xg_n_max, sizeof(float) * n);
@@ -632,6 +743,7 @@ static int xg_fetch(mcb200_ctx* c, int n, int n_est, float* const* out, float* c
 }
 
 extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float* put_out, float* call_se, float* put_se) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_results");
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -642,6 +754,7 @@ extern "C" int mcb200_xgpu_results(mcb200_ctx* c, int n, float* call_out, float*
 
 extern "C" int mcb200_xgpu_results_greeks(mcb200_ctx* c, int n, float* const out[MCB200_N_GREEK_OUTPUTS],
                                           float* const out_se[MCB200_N_GREEK_OUTPUTS]) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_xgpu_results_greeks");
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -654,6 +767,15 @@ constexpr int kDirectWriteMaxOptions = 4096;
 static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps, float num_trials, int payoff,
                     int stream_mode, Bumps bumps, const uint8_t* chunk_seeds_host, float* const* out,
                     float* const* out_se, float* growth_out_host, bool dump) {
+    if (c && c->multi) {
+        if (stream_mode != STREAM_FAST || dump)
+            return fail(MCB200_ERR_INVALID, "reference-stream / dump modes run on one device: use mcb200_ctx_child");
+        if (n < 0) return fail(MCB200_ERR_INVALID, "n = %d < 0", n);
+        if (n > 0) for (int i = 0; i < 6; ++i) if (!in[i]) return fail(MCB200_ERR_INVALID, "null input array %d", i);
+        const mcb200_bumps mb{bumps.dspot, bumps.dvol, bumps.drate, bumps.dyears};
+        return multi_run_host(c->multi, n, in, steps, num_trials, payoff == PAYOFF_GREEKS ? 1 : 0,
+                              payoff == PAYOFF_AV ? MCB200_ANTITHETIC : 0u, &mb, out, out_se);
+    }
     int rc = check_common(c, n, in, 6);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -725,6 +847,75 @@ static int run_host(mcb200_ctx* c, int n, const float* const in[6], float steps,
     }
     return MCB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ trials-minor building blocks
+namespace mcb200 {
+
+int host_moments(mcb200_ctx* c, int n, const float* const in[6], float steps, float num_trials_local, int greeks,
+                 unsigned flags, const mcb200_bumps* bumps, double* moments_host) {
+    int rc = check_common(c, n, in, 6);
+    if (rc) return rc;
+    if (n == 0) return MCB200_OK;
+    if (!moments_host) return fail(MCB200_ERR_INVALID, "null moments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const int n_acc = 2 * (greeks ? EST_COUNT_GREEKS : EST_COUNT_PRICE);
+    const size_t in_f = 6 * (size_t)n;
+    if ((rc = ensure_stage(c, in_f))) return rc;
+    if ((rc = ensure(&c->moments, &c->moments_cap, (size_t)n * n_acc))) return rc;
+    cudaStream_t st = c->stream;
+    for (int k = 0; k < 6; ++k) std::memcpy(c->h_stage + (size_t)k * n, in[k], sizeof(float) * n);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
+    const float* d = c->d_stage;
+    Request rq;
+    rq.n = n; rq.steps = steps; rq.num_trials = num_trials_local;
+    rq.payoff = greeks ? PAYOFF_GREEKS : ((flags & MCB200_ANTITHETIC) ? PAYOFF_AV : PAYOFF_PRICE);
+    if (bumps) rq.bumps = to_bumps(bumps);
+    rq.opt = OptionArrays{d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n};
+    rc = run_sim(c, rq, c->moments, false, nullptr, nullptr, st, nullptr);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(moments_host, c->moments, sizeof(double) * (size_t)n * n_acc, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MCB200_OK;
+}
+
+int host_finalize(mcb200_ctx* c, int n, int greeks, const float* rate, const float* years, const double* moments_host,
+                  double total_paths, double total_num_trials, const mcb200_bumps* bumps, float* const* out,
+                  float* const* out_se) {
+    const float* in[2] = {rate, years};
+    int rc = check_common(c, n, in, 2);
+    if (rc) return rc;
+    if (n == 0) return MCB200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const int n_est = greeks ? EST_COUNT_GREEKS : EST_COUNT_PRICE;
+    const int n_acc = 2 * n_est;
+    const size_t in_f = 2 * (size_t)n, out_f = (size_t)n_acc * n;
+    if ((rc = ensure_stage(c, in_f + out_f))) return rc;
+    if ((rc = ensure(&c->moments, &c->moments_cap, (size_t)n * n_acc))) return rc;
+    cudaStream_t st = c->stream;
+    std::memcpy(c->h_stage, rate, sizeof(float) * n);
+    std::memcpy(c->h_stage + n, years, sizeof(float) * n);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(float) * in_f, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->moments, moments_host, sizeof(double) * (size_t)n * n_acc, cudaMemcpyHostToDevice, st));
+    float* d_out[EST_COUNT_GREEKS]; float* d_se[EST_COUNT_GREEKS];
+    for (int e = 0; e < n_est; ++e) {
+        d_out[e] = c->d_stage + in_f + (size_t)e * n;
+        d_se[e] = c->d_stage + in_f + (size_t)(n_est + e) * n;
+    }
+    rc = run_finalize(c, n, n_est, c->moments, total_paths, total_num_trials, c->d_stage, c->d_stage + n,
+                      bumps ? to_bumps(bumps) : Bumps{1, 1, 1, 1}, d_out, d_se, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(c->h_stage + in_f, c->d_stage + in_f, sizeof(float) * out_f, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int e = 0; e < n_est; ++e) {
+        if (out && out[e]) std::memcpy(out[e], c->h_stage + in_f + (size_t)e * n, sizeof(float) * n);
+        if (out_se && out_se[e]) std::memcpy(out_se[e], c->h_stage + in_f + (size_t)(n_est + e) * n, sizeof(float) * n);
+    }
+    return MCB200_OK;
+}
+
+}  // namespace mcb200
 
 extern "C" int mcb200_price_batch(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
                                   const float* rate, const float* years, const float* div, float steps,
@@ -811,6 +1002,7 @@ extern "C" int mcb200_bs_batch_device(mcb200_ctx* c, int n, const float* spot, c
 extern "C" int mcb200_bs_batch(mcb200_ctx* c, int n, const float* spot, const float* strike, const float* vol,
                                const float* rate, const float* years, const float* div,
                                float* const out[MCB200_N_GREEK_OUTPUTS]) {
+    if (c && c->multi) return mcb200_bs_batch(multi_child(c->multi, 0), n, spot, strike, vol, rate, years, div, out);
     const float* in[6] = {spot, strike, vol, rate, years, div};
     int rc = check_common(c, n, in, 6);
     if (rc) return rc;
@@ -836,6 +1028,7 @@ extern "C" int mcb200_bs_batch(mcb200_ctx* c, int n, const float* spot, const fl
 }
 
 extern "C" int mcb200_ctx_export_states(mcb200_ctx* c, int64_t first, int64_t count, uint64_t* states_out) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_ctx_export_states");
     if (!c || !states_out) return fail(MCB200_ERR_INVALID, "null argument");
     if (first < 0 || count < 0 || first + count > c->pool_threads)
         return fail(MCB200_ERR_INVALID, "state range [%lld,%lld) outside pool of %lld", (long long)first,
@@ -848,6 +1041,7 @@ extern "C" int mcb200_ctx_export_states(mcb200_ctx* c, int64_t first, int64_t co
 }
 
 extern "C" int mcb200_ctx_set_timing(mcb200_ctx* c, int enabled) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_ctx_set_timing");
     if (!c) return fail(MCB200_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
@@ -858,6 +1052,7 @@ extern "C" int mcb200_ctx_set_timing(mcb200_ctx* c, int enabled) {
 }
 
 extern "C" int mcb200_ctx_last_sim_ms(mcb200_ctx* c, float* ms_out) {
+    SINGLE_DEVICE_ONLY(c, "mcb200_ctx_last_sim_ms");
     if (!c || !ms_out) return fail(MCB200_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->timing || !c->timed_once) return fail(MCB200_ERR_INVALID, "no timed simulate-kernel launch recorded");
@@ -878,6 +1073,7 @@ extern "C" int mcb200_debug_set_trace(mcb200_ctx* c, unsigned long long* device_
 
 extern "C" int mcb200_microbench(mcb200_ctx* c, mcb200_pipe_rate* out, int cap) {
     if (!c || !out || cap <= 0) return -fail(MCB200_ERR_INVALID, "bad microbench arguments");
+    if (c->multi) return mcb200_microbench(multi_child(c->multi, 0), out, cap);
     std::lock_guard<std::mutex> lk(c->mu);
     if (cudaSetDevice(c->device) != cudaSuccess) return -fail(MCB200_ERR_CUDA, "cudaSetDevice failed");
     int n = run_microbench(c->stream, c->sm_count, out, cap);
@@ -887,28 +1083,62 @@ extern "C" int mcb200_microbench(mcb200_ctx* c, mcb200_pipe_rate* out, int cap) 
 }
 
 // ------------------------------------------------------------------------------------------------ default context + drop-ins
-static mcb200_ctx* g_default = nullptr;
+// Shared ownership: a drop-in holds a reference for the duration of its call, so mcb200_default_ctx_reset() on another
+// thread retires the old context only after the last call using it has returned.
+static std::shared_ptr<mcb200_ctx> g_default;
 static std::mutex g_default_mu;
 
-extern "C" int mcb200_default_ctx(mcb200_ctx** out) {
+static int default_ctx_ref(std::shared_ptr<mcb200_ctx>* out) {
     std::lock_guard<std::mutex> lk(g_default_mu);
     if (!g_default) {
         const char* dev = std::getenv("MCB200_DEVICE");
+        const char* devs = std::getenv("MCB200_DEVICES");        // e.g. "0,1,2,3": a multi-device default context
         const char* seed = std::getenv("MCB200_SEED");
         const char* blk = std::getenv("MCB200_SUBSTREAM_BLOCK");
-        int rc = mcb200_ctx_create(&g_default, dev ? std::atoi(dev) : 0,
-                                   seed ? std::strtoull(seed, nullptr, 0) : 0x5EED5EED5EED5EEDull,
-                                   blk ? (uint32_t)std::strtoul(blk, nullptr, 0) : 0u);
+        const uint64_t sd = seed ? std::strtoull(seed, nullptr, 0) : 0x5EED5EED5EED5EEDull;
+        const uint32_t bk = blk ? (uint32_t)std::strtoul(blk, nullptr, 0) : 0u;
+        mcb200_ctx* raw = nullptr;
+        int rc;
+        if (devs && *devs) {
+            int ids[64], n = 0;
+            for (const char* p = devs; *p && n < 64;) {
+                char* end = nullptr;
+                long v = std::strtol(p, &end, 10);
+                if (end == p) break;
+                ids[n++] = (int)v;
+                p = (*end == ',') ? end + 1 : end;
+            }
+            rc = mcb200_ctx_create_multi(&raw, ids, n, sd, bk);
+        } else {
+            rc = mcb200_ctx_create(&raw, dev ? std::atoi(dev) : 0, sd, bk);
+        }
         if (rc != MCB200_OK) return rc;
+        g_default = std::shared_ptr<mcb200_ctx>(raw, [](mcb200_ctx* p) { mcb200_ctx_destroy(p); });
     }
-    if (out) *out = g_default;
+    *out = g_default;
+    return MCB200_OK;
+}
+
+extern "C" int mcb200_default_ctx(mcb200_ctx** out) {
+    std::shared_ptr<mcb200_ctx> ref;
+    int rc = default_ctx_ref(&ref);
+    if (rc != MCB200_OK) return rc;
+    if (out) *out = ref.get();             // borrowed: valid until the next mcb200_default_ctx_reset()
     return MCB200_OK;
 }
 
 extern "C" int mcb200_default_ctx_reset(int device, uint64_t seed, uint32_t substream_block) {
-    std::lock_guard<std::mutex> lk(g_default_mu);
-    if (g_default) { mcb200_ctx_destroy(g_default); g_default = nullptr; }
-    return mcb200_ctx_create(&g_default, device, seed, substream_block);
+    mcb200_ctx* raw = nullptr;
+    int rc = mcb200_ctx_create(&raw, device, seed, substream_block);
+    if (rc != MCB200_OK) return rc;
+    std::shared_ptr<mcb200_ctx> fresh(raw, [](mcb200_ctx* p) { mcb200_ctx_destroy(p); });
+    std::shared_ptr<mcb200_ctx> old;
+    {
+        std::lock_guard<std::mutex> lk(g_default_mu);
+        old.swap(g_default);
+        g_default = fresh;
+    }
+    return MCB200_OK;                      // `old` is destroyed here, or when the last drop-in using it returns
 }
 
 static const float kNaN = std::numeric_limits<float>::quiet_NaN();
@@ -916,8 +1146,9 @@ static const float kNaN = std::numeric_limits<float>::quiet_NaN();
 // One option through the batched path; `which` picks the estimator to return.
 static float dropin_price(float spot, float strike, float vol, float rate, float years, float div, float steps,
                           float num_trials, unsigned flags, int which) {
-    mcb200_ctx* c = nullptr;
-    if (mcb200_default_ctx(&c) != MCB200_OK) return kNaN;
+    std::shared_ptr<mcb200_ctx> ref;
+    if (default_ctx_ref(&ref) != MCB200_OK) return kNaN;
+    mcb200_ctx* c = ref.get();
     float outv[2] = {kNaN, kNaN};
     int rc = mcb200_price_batch(c, 1, &spot, &strike, &vol, &rate, &years, &div, steps, num_trials, flags, &outv[0],
                                 &outv[1], nullptr, nullptr);
@@ -926,8 +1157,9 @@ static float dropin_price(float spot, float strike, float vol, float rate, float
 
 static float dropin_greek(float spot, float strike, float vol, float rate, float years, float div, float steps,
                           float num_trials, mcb200_bumps bumps, int which) {
-    mcb200_ctx* c = nullptr;
-    if (mcb200_default_ctx(&c) != MCB200_OK) return kNaN;
+    std::shared_ptr<mcb200_ctx> ref;
+    if (default_ctx_ref(&ref) != MCB200_OK) return kNaN;
+    mcb200_ctx* c = ref.get();
     float vals[MCB200_N_GREEK_OUTPUTS];
     float* out[MCB200_N_GREEK_OUTPUTS];
     for (int e = 0; e < MCB200_N_GREEK_OUTPUTS; ++e) { vals[e] = kNaN; out[e] = (e == which) ? &vals[e] : nullptr; }

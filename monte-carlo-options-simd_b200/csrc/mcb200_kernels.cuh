@@ -330,16 +330,19 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (lane == i) mine = v;
         }
+        // A (warp, option) segment longer than kMaxRoundsPerFlush rounds is flushed in pieces that accumulate in the
+        // slot; a segment that ends with its first flush (the common case) touches the slot only if other warps share
+        // the option -- an option owned by one warp alone is finalised straight from registers.
+        const long long first_round = (long long)o * a.rounds_per_option;
+        const int w_first = owner_warp(first_round, R, W);
+        const int w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
+        const bool solo = (w_first == w_last);               // the whole option lives in this warp's range
         double* slot = a.slots + ((size_t)w + (size_t)o) * kAcc;
         if (lane < kAcc) {
             if (!fresh) mine += slot[lane];                  // only this warp touches the slot before its arrival
-            slot[lane] = mine;
+            if (!(solo && segment_done)) slot[lane] = mine;
         }
         if (segment_done) {
-            const long long first_round = (long long)o * a.rounds_per_option;
-            const int w_first = owner_warp(first_round, R, W);
-            const int w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
-            const bool solo = (w_first == w_last);           // the whole option lives in this warp's range
             bool complete = solo;
             double s = mine;                                 // lane i < kAcc holds accumulator i
             if (!solo) {

@@ -17,10 +17,13 @@ static inline long long ceil_div(long long a, long long b) { return (a + b - 1) 
 
 int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan* out) {
     if (!out || n_options < 0 || grid_slots <= 0) return MCB200_ERR_INVALID;
-    if (!(steps >= 1.0f) || !(num_trials >= 0.0f) || !std::isfinite(steps) || !std::isfinite(num_trials))
-        return MCB200_ERR_INVALID;
-    if (steps > 2.0e9f || num_trials > 2.0e9f) return MCB200_ERR_INVALID;
-    const long long n_paths = 8ll * ((long long)num_trials / 8);        // (num_trials as i32) / 8 chunks of 8
+    // steps in (0,1) and negative num_trials are legal in the reference: no normals are drawn / the chunk range is
+    // empty (mc_simd.rs:47,49) and a finite value comes back.  steps <= 0 gives dt = T/steps = inf or NaN there; here
+    // it is refused (the drop-ins return NaN either way).
+    if (!(steps > 0.0f) || !std::isfinite(steps) || !std::isfinite(num_trials)) return MCB200_ERR_INVALID;
+    if (steps > 2.0e9f || num_trials > 2.0e9f || num_trials < -2.0e9f) return MCB200_ERR_INVALID;
+    const long long chunks = (long long)num_trials / 8;                 // (num_trials as i32) / 8 chunks of 8
+    const long long n_paths = chunks > 0 ? 8ll * chunks : 0;            // an empty or negative range simulates nothing
     const int half_steps = (int)steps / 2;                              // (steps as i32) / 2
     mcb200_plan p{};
     p.n_paths = (int)n_paths;
@@ -42,6 +45,42 @@ int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb2
     return MCB200_OK;
 }
 
+// Sharding policy of a batch over `n_shards` GPUs (one process with several devices, or one process per GPU): replaces
+// the reference's single fan-out over a thread pool (mc_simd.rs:49-51) and its reduce (mc_simd.rs:71-74) at node scale.
+//   single         the batch does not fill one GPU (rounds <= its resident warps), or one shard: shard 0 runs it alone;
+//   options-major  n >= 16 * n_shards: contiguous blocks of options, no exchange (imbalance <= 1/16);
+//   trials-minor   otherwise: every shard simulates a contiguous range of the 8-path chunks of ALL options; the fp64
+//                  moment sums are added in shard order and finalised once.
+int make_shard(int n_options, float steps, float num_trials, int n_shards, int shard, int grid_slots, mcb200_shard* out) {
+    if (!out || n_shards <= 0 || shard < 0 || shard >= n_shards) return MCB200_ERR_INVALID;
+    mcb200_plan whole;
+    int rc = make_plan(n_options, steps, num_trials, grid_slots, &whole);
+    if (rc != MCB200_OK) return rc;
+    mcb200_shard s{};
+    s.n_shards = n_shards; s.shard = shard;
+    s.total_paths = (double)whole.n_paths;
+    const long long chunks = whole.n_paths / 8;
+    const long long resident = (long long)grid_slots * kPlanWarps;
+    if (n_shards == 1 || n_options == 0 || chunks == 0 || whole.total_rounds <= resident) {
+        s.mode = MCB200_SHARD_SINGLE;
+        if (shard == 0) { s.option_begin = 0; s.option_end = n_options; s.num_trials_local = num_trials; s.active = 1; }
+    } else if ((long long)n_options >= 16ll * n_shards) {
+        s.mode = MCB200_SHARD_OPTIONS;
+        s.option_begin = (int)((long long)shard * n_options / n_shards);
+        s.option_end = (int)(((long long)shard + 1) * n_options / n_shards);
+        s.num_trials_local = num_trials;
+        s.active = s.option_end > s.option_begin;
+    } else {
+        s.mode = MCB200_SHARD_TRIALS;
+        const long long c0 = shard * chunks / n_shards, c1 = ((long long)shard + 1) * chunks / n_shards;
+        s.option_begin = 0; s.option_end = n_options;
+        s.num_trials_local = (float)(8 * (c1 - c0));
+        s.active = c1 > c0;
+    }
+    *out = s;
+    return MCB200_OK;
+}
+
 void plan_warp_range(const mcb200_plan* p, int warp, long long* first, long long* last) {
     *first = (long long)warp * p->total_rounds / p->warps;
     *last = ((long long)warp + 1) * p->total_rounds / p->warps;
@@ -51,6 +90,11 @@ void plan_warp_range(const mcb200_plan* p, int warp, long long* first, long long
 
 extern "C" int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan* out) {
     return mcb200::make_plan(n_options, steps, num_trials, grid_slots, out);
+}
+
+extern "C" int mcb200_shard_query(int n_options, float steps, float num_trials, int n_shards, int shard, int grid_slots,
+                                  mcb200_shard* out) {
+    return mcb200::make_shard(n_options, steps, num_trials, n_shards, shard, grid_slots, out);
 }
 
 extern "C" int mcb200_plan_warp_range(const mcb200_plan* plan, int warp, int64_t* first_round, int64_t* end_round) {

@@ -13,10 +13,10 @@ import numpy as np
 
 
 def partition_options(n_options, world_size, rank):
-    """Contiguous block [lo, hi) of the batch owned by `rank` (sizes differ by at most one)."""
-    base, rem = divmod(int(n_options), int(world_size))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Contiguous block [lo, hi) of the batch owned by `rank` (sizes differ by at most one): the options-major split of
+    mcb200_shard_query."""
+    n, w, r = int(n_options), int(world_size), int(rank)
+    return r * n // w, (r + 1) * n // w
 
 
 def partition_trials(num_trials, world_size, rank):
@@ -24,9 +24,9 @@ def partition_trials(num_trials, world_size, rank):
 
     Returns (local_num_trials, total_paths): the local count is a multiple of 8; total_paths = 8*floor(num_trials/8)
     is what all ranks simulate together, so the sharded estimator equals the single-GPU one in distribution."""
-    chunks = int(num_trials) // 8
-    base, rem = divmod(chunks, int(world_size))
-    mine = base + (1 if rank < rem else 0)
+    chunks = max(int(num_trials) // 8, 0)
+    w, r = int(world_size), int(rank)
+    mine = (r + 1) * chunks // w - r * chunks // w          # the trials-minor split of mcb200_shard_query
     return 8 * mine, 8 * chunks
 
 

@@ -15,6 +15,13 @@ int main(int argc, char **argv) {
     if (mcb200_plan_warp_range(&p, p.warps - 1, &a, &b) != MCB200_OK || b != p.total_rounds) return 12;
     if (mcb200_plan_query(1, 0.0f, 1000.0f, 592, &p) != MCB200_ERR_INVALID) return 13;
 
+    mcb200_shard sh;                                                /* 8 GPUs: few options -> trials-minor; a sweep -> options-major */
+    if (mcb200_shard_query(8, 100.0f, 8e6f, 8, 3, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_TRIALS ||
+        sh.num_trials_local != 1e6f || sh.total_paths != 8e6) return 14;
+    if (mcb200_shard_query(100000, 252.0f, 1e4f, 8, 7, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_OPTIONS ||
+        sh.option_begin != 87500 || sh.option_end != 100000) return 15;
+    if (mcb200_shard_query(1, 100.0f, 1000.0f, 8, 1, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_SINGLE || sh.active) return 16;
+
     const int want_gpu = argc > 1 && strcmp(argv[1], "gpu") == 0;
     float v = mc_simd_call_price(100.0f, 110.0f, 0.25f, 0.05f, 0.5f, 0.02f, 100.0f, 20000.0f);
     if (!want_gpu) {
@@ -22,6 +29,8 @@ int main(int argc, char **argv) {
         if (strstr(mcb200_last_error(), "no CPU path") == NULL) return 21;
         mcb200_ctx *ctx = NULL;
         if (mcb200_ctx_create(&ctx, 0, 1u, 0u) != MCB200_ERR_NO_DEVICE || ctx != NULL) return 22;
+        int devs0[2] = {0, 1};
+        if (mcb200_ctx_create_multi(&ctx, devs0, 2, 1u, 0u) != MCB200_ERR_NO_DEVICE || ctx != NULL) return 23;
         printf("c client ok (no device): %s\n", mcb200_last_error());
         return 0;
     }
@@ -37,6 +46,23 @@ int main(int argc, char **argv) {
     if (mcb200_bs_batch(ctx, 3, spot, strike, vol, rate, years, div, bs_out) != MCB200_OK) return 33;
     for (int i = 0; i < 3; ++i)
         if (fabsf(call[i] - bs_call[i]) > 4.0f * cse[i] + 1e-3f) { printf("%d: %f vs %f +- %f\n", i, call[i], bs_call[i], cse[i]); return 34; }
+    /* the multi-device context behind the same host-buffer call: two per-device contexts (here both on device 0, on
+     * substream blocks 0 and 1); 3 options x 400000 trials -> trials-minor split, host sum in device order */
+    int devs[2] = {0, 0};
+    mcb200_ctx *multi = NULL;
+    if (mcb200_ctx_create_multi(&multi, devs, 2, 1234u, 0u) != MCB200_OK) { printf("%s\n", mcb200_last_error()); return 40; }
+    if (mcb200_ctx_device_count(multi) != 2 || mcb200_ctx_device_count(ctx) != 1) return 41;
+    float call2[3], put2[3], cse2[3], pse2[3];
+    if (mcb200_price_batch(multi, 3, spot, strike, vol, rate, years, div, 100.0f, 400000.0f, 0u, call2, put2, cse2, pse2) != MCB200_OK) {
+        printf("%s\n", mcb200_last_error()); return 42;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (fabsf(call2[i] - bs_call[i]) > 4.0f * cse2[i] + 1e-3f) { printf("multi %d: %f vs %f +- %f\n", i, call2[i], bs_call[i], cse2[i]); return 43; }
+        if (!(cse2[i] < 0.45f * cse[i])) return 44;                 /* ten times the trials: SE shrinks by sqrt(10) */
+    }
+    if (mcb200_price_batch_device(multi, 3, spot, strike, vol, rate, years, div, 100.0f, 1000.0f, 0u, call2, put2, cse2, pse2, 0)
+        != MCB200_ERR_INVALID) return 45;                           /* device pointers belong to one device */
+    mcb200_ctx_destroy(multi);
     mcb200_ctx_destroy(ctx);
     printf("c client ok (gpu): call %.4f %.4f %.4f  drop-in %.4f\n", call[0], call[1], call[2], v);
     return 0;

@@ -12,9 +12,14 @@ from conftest import ROOT, load_package
 
 
 def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "mcb200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mcb200_[a-z0-9_]+|mc_simd_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not header.endswith(".h"):
+            continue
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(mcb200_[a-z0-9_]+|mc_simd_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -102,10 +107,46 @@ def test_planner_fills_the_machine(pkg):
 
 
 def test_planner_rejects_bad_requests(pkg):
-    for n, steps, trials in [(-1, 100.0, 1000.0), (1, 0.0, 1000.0), (1, float("nan"), 1000.0), (1, 100.0, -8.0),
-                             (1, 100.0, float("inf")), (1, 1e10, 1000.0)]:
+    for n, steps, trials in [(-1, 100.0, 1000.0), (1, 0.0, 1000.0), (1, -2.0, 1000.0), (1, float("nan"), 1000.0),
+                             (1, 100.0, float("inf")), (1, 1e10, 1000.0), (1, 100.0, float("nan"))]:
         with pytest.raises(pkg.Mcb200Error):
             pkg.plan_query(n, steps, trials, 1184)
+    # legal in the reference, finite results there: no normals for steps in (0,1) (mc_simd.rs:47), an empty chunk range
+    # for negative trial counts (mc_simd.rs:49)
+    assert pkg.plan_query(1, 0.5, 1000.0, 1184)["half_steps"] == 0
+    assert pkg.plan_query(3, 100.0, -8.0, 1184)["n_paths"] == 0 and pkg.plan_query(3, 100.0, -8.0, 1184)["grid"] == 0
+
+
+def test_shard_policy(pkg):
+    """mcb200_shard_query: single device when the batch does not fill one GPU, options-major blocks for >= 16 options per
+    GPU, trials-minor chunk ranges otherwise; the shards tile the batch exactly once."""
+    slots = 592
+    for n, steps, trials, world, mode in [(112, 100.0, 1000.0, 8, "single"), (1, 100.0, 1000.0, 4, "single"),
+                                          (112, 100.0, 20000.0, 8, "trials"), (112, 100.0, 20000.0, 2, "options"),
+                                          (100000, 252.0, 1e4, 8, "options"), (100000, 252.0, 1e6, 7, "options"),
+                                          (8, 100.0, 8e6, 8, "trials"), (4096, 252.0, 1e5, 8, "options"),
+                                          (5, 50.0, 1000003.0, 3, "trials"), (100, 10.0, 1e6, 1, "single")]:
+        shards = [pkg.shard_query(n, steps, trials, world, r, slots) for r in range(world)]
+        assert all(s["mode"] == mode for s in shards), (n, trials, world, shards[0]["mode"])
+        paths = 8 * (int(trials) // 8)
+        assert all(s["total_paths"] == paths for s in shards)
+        if mode == "single":
+            assert shards[0]["active"] and (shards[0]["option_begin"], shards[0]["option_end"]) == (0, n)
+            assert shards[0]["num_trials_local"] == np.float32(trials) and not any(s["active"] for s in shards[1:])
+        elif mode == "options":
+            assert shards[0]["option_begin"] == 0 and shards[-1]["option_end"] == n
+            assert all(shards[i]["option_end"] == shards[i + 1]["option_begin"] for i in range(world - 1))
+            sizes = [s["option_end"] - s["option_begin"] for s in shards]
+            assert max(sizes) - min(sizes) <= 1 and all(s["num_trials_local"] == np.float32(trials) for s in shards)
+            lo, hi = pkg.sharding.partition_options(n, world, 1 % world)
+            assert (lo, hi) == (shards[1 % world]["option_begin"], shards[1 % world]["option_end"])
+        else:
+            assert all((s["option_begin"], s["option_end"]) == (0, n) for s in shards)
+            local = [s["num_trials_local"] for s in shards]
+            assert all(t % 8 == 0 for t in local) and sum(local) == paths and max(local) - min(local) <= 8
+            assert [pkg.sharding.partition_trials(trials, world, r)[0] for r in range(world)] == local
+    with pytest.raises(pkg.Mcb200Error):
+        pkg.shard_query(10, 100.0, 1000.0, 4, 4, slots)
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
@@ -177,15 +218,26 @@ def test_jump_table_doubling_chain(oracle):
     """include/xoshiro256_jump_tables.h: entry k applied twice == entry k+1 applied once, starting from the published
     JUMP polynomial (entry 0); so entry k really is jump^(2^k)."""
     text = open(os.path.join(ROOT, "include", "xoshiro256_jump_tables.h")).read()
-    rows = re.findall(r"\{(0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL\}", text)
-    table = [[int(x, 16) for x in r] for r in rows]
+    def rows_of(name):
+        body = re.search(name + r"\[\d*\]\[4\] = \{(.*?)\};", text, flags=re.S).group(1)
+        rows = re.findall(r"\{(0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL, (0x[0-9a-f]+)ULL\}", body)
+        return [[int(x, 16) for x in r] for r in rows]
+    table, long_table = rows_of("XOSHIRO256_JUMP_POW2"), rows_of("XOSHIRO256_LONG_JUMP_POW2")
+    long_jump = [0x76e15d3efefdcbbf, 0xc5004e441c522fb3, 0x77710069854ee241, 0x39109bb02acbe635]
     assert table[0] == [0x180ec6d33cfd0aba, 0xd5a61266f0c9392c, 0xa9582618e03fc9aa, 0x39abdc4529b1661c]
-    assert table[-1] == [0x76e15d3efefdcbbf, 0xc5004e441c522fb3, 0x77710069854ee241, 0x39109bb02acbe635]  # LONG_JUMP
+    assert len(table) == 40 and len(long_table) == 32 and long_table[0] == long_jump
     state = [0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9, 0x94d049bb133111eb, 0x2545f4914f6cdd1d]
-    for k in range(0, 24):
-        twice = oracle.xoshiro_apply_poly(oracle.xoshiro_apply_poly(state, table[k]), table[k])
-        once = oracle.xoshiro_apply_poly(state, table[k + 1])
-        assert list(twice) == list(once), k
+    for tab, upto in ((table, 24), (long_table, 31)):
+        for k in range(0, upto):
+            twice = oracle.xoshiro_apply_poly(oracle.xoshiro_apply_poly(state, tab[k]), tab[k])
+            once = oracle.xoshiro_apply_poly(state, tab[k + 1])
+            assert list(twice) == list(once), k
+    # substream block b = long_jump applied b times = the set bits of b through the power table (what seed_pool does)
+    serial = list(state)
+    for _ in range(5):
+        serial = list(oracle.xoshiro_apply_poly(serial, long_jump))
+    fast = list(oracle.xoshiro_apply_poly(oracle.xoshiro_apply_poly(state, long_table[0]), long_table[2]))
+    assert serial == fast
 
 
 def test_sharding_partitions(pkg):

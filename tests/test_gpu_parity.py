@@ -311,8 +311,15 @@ def test_empty_and_degenerate_inputs(pkg, ctx):
     fwd = 100.0 * math.exp(0.05 - 0.5 * 0.04) - 90.0
     assert d["call"][0] == pytest.approx(fwd * math.exp(-0.05), rel=1e-5)
     assert d["call_se"][0] <= 2e-3 * d["call"][0]      # fp32 sum of squares: variance resolved to ~1e-7 * mean^2
+    # steps in (0,1): (steps as i32)/2 = 0 pairs, drift = steps * nudt with dt = T/steps (mc_simd.rs:36-47): the same
+    # deterministic forward, like the reference
+    h = ctx.price_batch([100.0], 90.0, 0.2, 0.05, 1.0, 0.0, 0.5, 64.0)
+    assert h["call"][0] == pytest.approx(fwd * math.exp(-0.05), rel=1e-5)
+    # a negative trial count is an empty chunk range in the reference (mc_simd.rs:49): sum 0, price 0 (here -0.0)
+    neg = ctx.price_batch([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, 100.0, -16.0)
+    assert neg["call"][0] == 0.0 and neg["call_se"][0] == 0.0
     for bad in [dict(steps=0.0, num_trials=1000.0), dict(steps=float("nan"), num_trials=1000.0),
-                dict(steps=100.0, num_trials=-1.0)]:
+                dict(steps=-3.0, num_trials=1000.0), dict(steps=100.0, num_trials=float("inf"))]:
         with pytest.raises(pkg.Mcb200Error):
             ctx.price_batch([100.0], 100.0, 0.2, 0.05, 1.0, 0.0, bad["steps"], bad["num_trials"])
     assert math.isnan(pkg.mc_simd.call_price(100.0, 100.0, 0.2, 0.05, 1.0, 0.0, 0.0, 1000.0))

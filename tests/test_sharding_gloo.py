@@ -76,4 +76,4 @@ def test_trials_sharding_world2_gloo(tmp_path, oracle, pkg):
         n = 8 * (int(PARAMS["trials"]) // 8)
         var = (whole[1] - whole[0] ** 2 / n) / (n - 1)
         assert got["call_se"][i] == pytest.approx(math.sqrt(var / n) * n / PARAMS["trials"] * disc, rel=1e-5)
-    assert list(got["block"]) == [0, 2]                                      # options-major block of rank 0 of 2
+    assert list(got["block"]) == [0, 1]                                      # options-major block of rank 0 of 2: [0*3//2, 1*3//2)
