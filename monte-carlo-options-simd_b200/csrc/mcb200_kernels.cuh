@@ -232,6 +232,10 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 //     option's arrival counter; the warp that completes the count sums the option's slots in warp order (fixed order:
 //     bit-reproducible, independent of which warp arrives last) and writes moments and/or final values and SEs.
 // Path data never leaves registers.
+#ifndef MCB_LAZY_SLOT
+#define MCB_LAZY_SLOT(payoff) ((payoff) == PAYOFF_GREEKS)
+#endif
+
 #ifdef MCB_TRACE
 #define MCB_STAMP(k) do { if (a.trace && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); \
                                                      a.trace[(size_t)w * 8 + (k)] = t_; } } while (0)
@@ -331,18 +335,33 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
             if (lane == i) mine = v;
         }
         // A (warp, option) segment longer than kMaxRoundsPerFlush rounds is flushed in pieces that accumulate in the
-        // slot; a segment that ends with its first flush (the common case) touches the slot only if other warps share
-        // the option -- an option owned by one warp alone is finalised straight from registers.
-        const long long first_round = (long long)o * a.rounds_per_option;
-        const int w_first = owner_warp(first_round, R, W);
-        const int w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
-        const bool solo = (w_first == w_last);               // the whole option lives in this warp's range
+        // slot.  An option owned by one warp alone ("solo", most options of a large sweep) is finalised straight from
+        // registers: no fence, no arrival.  The Greeks kernel also skips the solo option's slot store (160 bytes); the
+        // price kernels keep that 32-byte store, because hoisting the ownership test above it makes ptxas schedule
+        // their path loop 3 % slower (profiles/r2_ab_kernel_variants.txt) -- the loop is ALU-pipe bound and its
+        // instruction order is what the time depends on.
+        constexpr bool kLazySlot = MCB_LAZY_SLOT(PAYOFF);
+        long long first_round = 0;
+        int w_first = 0, w_last = 0;
+        bool solo = false;                                   // the whole option lives in this warp's range
+        if (kLazySlot) {
+            first_round = (long long)o * a.rounds_per_option;
+            w_first = owner_warp(first_round, R, W);
+            w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
+            solo = (w_first == w_last);
+        }
         double* slot = a.slots + ((size_t)w + (size_t)o) * kAcc;
         if (lane < kAcc) {
             if (!fresh) mine += slot[lane];                  // only this warp touches the slot before its arrival
-            if (!(solo && segment_done)) slot[lane] = mine;
+            if (!kLazySlot || !(solo && segment_done)) slot[lane] = mine;
         }
         if (segment_done) {
+            if (!kLazySlot) {
+                first_round = (long long)o * a.rounds_per_option;
+                w_first = owner_warp(first_round, R, W);
+                w_last = owner_warp(first_round + a.rounds_per_option - 1, R, W);
+                solo = (w_first == w_last);
+            }
             bool complete = solo;
             double s = mine;                                 // lane i < kAcc holds accumulator i
             if (!solo) {

@@ -14,24 +14,25 @@ namespace mcb200 {
 
 constexpr int kThreads = 256;          // threads per CTA (8 warps, 2 per SM sub-partition)
 constexpr int kWarps = kThreads / 32;
-// Resident CTAs per SM and quads per loop iteration the path kernels are compiled for.  The inner step is bound by
-// the ALU pipe, not by latency (3.3 pairs/clk/SM at 8, 4 or 2 CTAs/SM alike for pair_fast, profiles/), so low occupancy
-// costs nothing and buys register-resident accumulators.  Measured with tools/tune_unroll_occupancy.sh:
-//   price / antithetic kernels: 4 CTAs/SM (64 registers), 2 quads per iteration   (C2 0.82, C5R 0.97 of the roofline)
-//   Greeks kernel (20 moment registers): 3 CTAs/SM (85 registers), 4 quads per iteration   (C4 0.93 instead of 0.88)
-// (round-1 figures, quad_fast).  The unroll factors count tri_fast calls (3 pairs each) per loop iteration.
+// Resident CTAs per SM and tri_fast calls (3 pairs each) per loop iteration the path kernels are compiled for.  The
+// inner step is bound by the ALU pipe, not by latency (4.3 pairs/clk/SM at 8 or 4 CTAs/SM alike, 4.1 at 2:
+// profiles/r2_microbench_tri_vs_quad.json), so low occupancy costs nothing and buys register-resident accumulators.
+// Measured with tools/ab_flags.sh (profiles/r2_ab_kernel_variants.txt), roofline.frac on C2 / C3 / C5R / C4:
+//   price / antithetic kernels: 4 CTAs/SM (64 registers); 2 -> 0.856 / 0.865 / 1.022, 4 -> 0.877 / 0.890 / 1.057,
+//                               8 tris per iteration -> 0.895 / 0.912 / 1.080 (5 CTAs/SM: 0.835 / 0.690 / 1.009)
+//   Greeks kernel (20 moment registers): 3 CTAs/SM; 4 tris per iteration -> C4 1.024, 6 -> 1.043, 8 -> 1.035
 // The MCB_* macros exist for that sweep only (MCB200_NVCC_FLAGS in build.py).
 #ifndef MCB_PRICE_CTAS
 #define MCB_PRICE_CTAS 4
 #endif
 #ifndef MCB_PRICE_UNROLL
-#define MCB_PRICE_UNROLL 2
+#define MCB_PRICE_UNROLL 8
 #endif
 #ifndef MCB_GREEKS_CTAS
 #define MCB_GREEKS_CTAS 3
 #endif
 #ifndef MCB_GREEKS_UNROLL
-#define MCB_GREEKS_UNROLL 4
+#define MCB_GREEKS_UNROLL 6
 #endif
 constexpr int kPriceCtasPerSm = MCB_PRICE_CTAS, kPriceQuadUnroll = MCB_PRICE_UNROLL;
 constexpr int kGreeksCtasPerSm = MCB_GREEKS_CTAS, kGreeksQuadUnroll = MCB_GREEKS_UNROLL;

@@ -114,3 +114,6 @@ double cpu_baseline_price_loop(int n, const float *spot, const float *strike, co
 }
 
 int cpu_baseline_threads(void) { return omp_get_max_threads(); }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the bench sets the team size explicitly to all host cores. */
+void cpu_baseline_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

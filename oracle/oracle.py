@@ -181,6 +181,8 @@ def baseline_lib():
         _base.cpu_baseline_price_loop.restype = _d
         _base.cpu_baseline_price_loop.argtypes = [C.c_int] + [_fp] * 6 + [_f, _f, C.c_int, C.c_uint64, _fp]
         _base.cpu_baseline_threads.restype = C.c_int
+        _base.cpu_baseline_set_threads.restype = None
+        _base.cpu_baseline_set_threads.argtypes = [C.c_int]
     return _base
 
 
@@ -196,3 +198,13 @@ def baseline_price_loop(spot, strike, vol, r, years, q, steps, num_trials, kind,
 
 def baseline_threads():
     return int(baseline_lib().cpu_baseline_threads())
+
+
+def baseline_use_all_cores():
+    """Set the OpenMP team to every core this process may run on (torchrun exports OMP_NUM_THREADS=1); returns it."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    baseline_lib().cpu_baseline_set_threads(n)
+    return baseline_threads()

@@ -56,3 +56,65 @@ def test_two_gpu_sharding(oracle):
     for key in ("call", "put", "call_se", "put_se"):
         assert fu[key] == tm[key], key
     assert out["greeks_fused_equals_nccl"] and all(g > 0 for g in out["greeks_fused_gamma"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_multi_device_context_on_two_real_gpus():
+    """mcb200_ctx_create_multi over devices [0, 1] (one process): the options-major blocks equal plain contexts on each
+    device bit for bit; a trials-minor batch equals moments(device 0) + moments(device 1) + one finalisation; and the
+    fused exchange buffer works between two same-process contexts on DIFFERENT devices (plain peer access)."""
+    from conftest import load_package
+    pkg = load_package()
+    G = (GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+    spots = np.linspace(70, 150, 64).astype(np.float32)
+    with pkg.Context(devices=[0, 1], seed=31) as multi:
+        got = multi.price_batch(spots, *G, 100.0, 80000.0)
+        few = multi.price_batch(spots[:4], *G, 100.0, 800000.0)
+        bs = multi.bs_batch(spots, *G)
+    for d, (lo, hi) in enumerate(((0, 32), (32, 64))):
+        with pkg.Context(device=d, seed=31, substream_block=d) as one:
+            want = one.price_batch(spots[lo:hi], *G, 100.0, 80000.0)
+        for k in want:
+            assert np.array_equal(got[k][lo:hi], want[k]), (d, k)
+    z = (got["call"] - bs["call"]) / np.maximum(got["call_se"], 1e-4)
+    assert np.abs(z).max() < 4.5
+    moms = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        cols = [torch.tensor(spots[:4], device=dev)] + [torch.full((4,), v, dtype=torch.float32, device=dev) for v in G]
+        with pkg.Context(device=d, seed=31, substream_block=d) as one:
+            with torch.cuda.device(dev):
+                # advance the substreams exactly like the multi context did (one options-major batch of 32 options)
+                one.price_batch(spots[32 * d:32 * d + 32], *G, 100.0, 80000.0)
+                m = torch.zeros(4, 4, dtype=torch.float64, device=dev)
+                one.price_moments_device(4, [c.data_ptr() for c in cols], 100.0, 400000.0, m.data_ptr())
+                torch.cuda.synchronize(dev)
+                moms.append(m.cpu())
+    total = (moms[0] + moms[1]).cuda(0)
+    dev0 = torch.device("cuda", 0)
+    rate = torch.full((4,), GRID["r"], dtype=torch.float32, device=dev0)
+    years = torch.full((4,), GRID["t"], dtype=torch.float32, device=dev0)
+    vals = torch.zeros(4, 4, device=dev0)
+    with pkg.Context(device=0, seed=1) as fin:
+        fin.price_finalize_device(4, rate.data_ptr(), years.data_ptr(), total.data_ptr(), 800000.0, 800000.0,
+                                  [vals[i].data_ptr() for i in range(4)])
+        torch.cuda.synchronize(dev0)
+    for i, k in enumerate(("call", "put", "call_se", "put_se")):
+        assert np.array_equal(few[k], vals[i].cpu().numpy()), k
+    # fused exchange buffer across two real devices of one process
+    n = 4
+    with pkg.Context(device=0, seed=77, substream_block=0) as c0, pkg.Context(device=1, seed=77, substream_block=1) as c1:
+        c0.xgpu_create(n, 2)
+        c1.xgpu_attach(c0, n, 2)
+        colsd = []
+        for d in (0, 1):
+            dev = torch.device("cuda", d)
+            colsd.append([torch.tensor(spots[:4], device=dev)] + [torch.full((4,), v, dtype=torch.float32, device=dev) for v in G])
+        for _ in range(3):
+            c0.price_xgpu_device(n, [c.data_ptr() for c in colsd[0]], 100.0, 200000.0, 0, 400000.0, 400000.0)
+            c1.price_xgpu_device(n, [c.data_ptr() for c in colsd[1]], 100.0, 200000.0, 1, 400000.0, 400000.0)
+            r0, r1 = c0.xgpu_results(n), c1.xgpu_results(n)
+            assert all(np.array_equal(r0[k], r1[k]) for k in r0)
+            assert np.all(np.abs(r0["call"] - bs["call"][:4]) <= 4.0 * r0["call_se"] + 1e-4)
+        c1.xgpu_close(); c0.xgpu_close()
