@@ -11,9 +11,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/mcb200.h"
 #include "../../include/xoshiro256_jump_tables.h"
@@ -41,6 +43,47 @@ static int fail(int code, const char* fmt, ...) {
             return fail(e_ == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA, "%s: %s (%s:%d)", #call, \
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
     } while (0)
+
+// ------------------------------------------------------------------------------------------------ device allocations
+// Production: plain cudaMalloc / cudaFree.  -DMCB_CHECKED builds (tools/checked_build.py; compute-sanitizer is closed
+// on the GPU pool this was developed on) put a 256-byte guard filled with 0xA5 on either side of every long-lived device
+// buffer of a context, and mcb200_debug_check() verifies the guards, the in-kernel index checks and that every
+// arrival counter is back to zero.
+#ifdef MCB_CHECKED
+static std::mutex g_guard_mu;
+static std::map<void*, size_t> g_guarded;          // user pointer -> user bytes
+constexpr size_t kGuard = 256;
+static cudaError_t dev_malloc(void** p, size_t bytes) {
+    char* raw = nullptr;
+    cudaError_t e = cudaMalloc((void**)&raw, bytes + 2 * kGuard);
+    if (e != cudaSuccess) return e;
+    cudaMemset(raw, 0xA5, kGuard);
+    cudaMemset(raw + kGuard + bytes, 0xA5, kGuard);
+    *p = raw + kGuard;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guarded[*p] = bytes;
+    return cudaSuccess;
+}
+static cudaError_t dev_free(void* p) {
+    if (!p) return cudaSuccess;
+    { std::lock_guard<std::mutex> lk(g_guard_mu); g_guarded.erase(p); }
+    return cudaFree((char*)p - kGuard);
+}
+static int guards_damaged() {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    int bad = 0;
+    unsigned char h[2 * kGuard];
+    for (auto& kv : g_guarded) {
+        cudaMemcpy(h, (char*)kv.first - kGuard, kGuard, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h + kGuard, (char*)kv.first + kv.second, kGuard, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < 2 * kGuard; ++i) if (h[i] != 0xA5) { ++bad; break; }
+    }
+    return bad;
+}
+#else
+static cudaError_t dev_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
+static cudaError_t dev_free(void* p) { return cudaFree(p); }
+#endif
 
 // ------------------------------------------------------------------------------------------------ host xoshiro (seeding only)
 struct HostXo { uint64_t s[4]; };
@@ -104,6 +147,9 @@ struct mcb200_ctx {
 #ifdef MCB_TRACE
     unsigned long long* trace = nullptr;    // device buffer of the timeline build (tools/kernel_timeline.py)
 #endif
+#ifdef MCB_CHECKED
+    unsigned* check = nullptr;              // device word: OR of the in-kernel index checks that failed
+#endif
     bool timing = false; bool timed_once = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     mcb200::MultiRuntime* multi = nullptr;   // non-null: this is the parent of a multi-device context (mcb200_multi.cu)
@@ -136,20 +182,20 @@ mcb200_ctx* ctx_new_parent(MultiRuntime* m, int device0, uint64_t seed, uint32_t
 
 static int ensure(double** p, size_t* cap, size_t need) {
     if (*cap >= need) return MCB200_OK;
-    if (*p) cudaFree(*p);
+    if (*p) dev_free(*p);
     *p = nullptr; *cap = 0;
     size_t want = need + need / 2 + 1024;
-    CU(cudaMalloc((void**)p, want * sizeof(double)));
+    CU(dev_malloc((void**)p, want * sizeof(double)));
     *cap = want;
     return MCB200_OK;
 }
 
 static int ensure_arrivals(mcb200_ctx* c, size_t need) {
     if (c->arrivals_cap >= need) return MCB200_OK;
-    if (c->arrivals) cudaFree(c->arrivals);
+    if (c->arrivals) dev_free(c->arrivals);
     c->arrivals = nullptr; c->arrivals_cap = 0;
     size_t want = need + need / 2 + 1024;
-    CU(cudaMalloc((void**)&c->arrivals, want * sizeof(unsigned)));
+    CU(dev_malloc((void**)&c->arrivals, want * sizeof(unsigned)));
     CU(cudaMemsetAsync(c->arrivals, 0, want * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));        // launches may arrive on caller streams
     c->arrivals_cap = want;
@@ -159,12 +205,12 @@ static int ensure_arrivals(mcb200_ctx* c, size_t need) {
 static int ensure_stage(mcb200_ctx* c, size_t need_floats) {
     if (c->stage_cap >= need_floats) return MCB200_OK;
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->d_stage) dev_free(c->d_stage);
     c->h_stage = nullptr; c->d_stage = nullptr; c->h_stage_dev = nullptr; c->stage_cap = 0;
     size_t want = need_floats + need_floats / 2 + 4096;
     CU(cudaHostAlloc((void**)&c->h_stage, want * sizeof(float), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void**)&c->h_stage_dev, c->h_stage, 0));
-    CU(cudaMalloc((void**)&c->d_stage, want * sizeof(float)));
+    CU(dev_malloc((void**)&c->d_stage, want * sizeof(float)));
     c->stage_cap = want;
     return MCB200_OK;
 }
@@ -241,7 +287,7 @@ extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, ui
         c->grid_slots = c->sm_count * occ;
         c->grid_slots_greeks = c->sm_count * occ_greeks;
         c->pool_threads = (int64_t)(c->grid_slots > c->grid_slots_greeks ? c->grid_slots : c->grid_slots_greeks) * kThreads;
-        if (cudaMalloc((void**)&c->pool, (size_t)c->pool_threads * 32) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "pool alloc failed"); break; }
+        if (dev_malloc((void**)&c->pool, (size_t)c->pool_threads * 32) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "pool alloc failed"); break; }
         if (cudaMalloc((void**)&c->d_jump, sizeof(XOSHIRO256_JUMP_POW2)) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "jump table alloc failed"); break; }
         if (cudaMemcpy(c->d_jump, XOSHIRO256_JUMP_POW2, sizeof(XOSHIRO256_JUMP_POW2), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "jump table copy failed"); break; }
         if ((rc = seed_pool(c))) break;
@@ -259,13 +305,16 @@ extern "C" void mcb200_ctx_destroy(mcb200_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->order_ev) cudaEventDestroy(c->order_ev);
-    if (c->pool) cudaFree(c->pool);
+    if (c->pool) dev_free(c->pool);
     if (c->d_jump) cudaFree(c->d_jump);
-    if (c->slots) cudaFree(c->slots);
-    if (c->arrivals) cudaFree(c->arrivals);
-    if (c->moments) cudaFree(c->moments);
+    if (c->slots) dev_free(c->slots);
+    if (c->arrivals) dev_free(c->arrivals);
+    if (c->moments) dev_free(c->moments);
+#ifdef MCB_CHECKED
+    if (c->check) cudaFree(c->check);
+#endif
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->d_stage) dev_free(c->d_stage);
     if (c->xg_base) { if (c->xg_owner) cudaFree(c->xg_base); else if (!c->xg_attached) cudaIpcCloseMemHandle(c->xg_base); }
     if (c->xg_status) cudaFree(c->xg_status);
     if (c->xg_event) cudaEventDestroy(c->xg_event);
@@ -393,6 +442,12 @@ static int run_sim(mcb200_ctx* c, const Request& rq, double* moments_out, bool f
     a.growth_out = rq.growth_out; a.one = 1u;
 #ifdef MCB_TRACE
     a.trace = c->trace;
+#endif
+#ifdef MCB_CHECKED
+    if (!c->check) { CU(cudaMalloc((void**)&c->check, sizeof(unsigned))); CU(cudaMemset(c->check, 0, sizeof(unsigned))); }
+    a.check = c->check; a.slots_cap = (unsigned long long)c->slots_cap; a.pool_threads = c->pool_threads;
+    if (std::getenv("MCB200_CHECK_INJECT")) a.slots_cap = 1;   // self-test of the detector: the slot check must fire
+    a.xg_doubles = rq.xg ? (unsigned long long)c->xg_world * c->xg_n_max * n_acc : 0ull;
 #endif
     if (rq.xg) {
         XgLayout L = xg_layout(c);
@@ -1061,6 +1116,27 @@ extern "C" int mcb200_ctx_last_sim_ms(mcb200_ctx* c, float* ms_out) {
     CU(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
     return MCB200_OK;
 }
+
+#ifdef MCB_CHECKED
+// bits: 1 pool index, 2 option index, 4 slot index, 8 arrival count, 16 final-sum index, 32 exchange-buffer index or
+// cross-GPU arrival count, 256 a guard region was overwritten, 512 an arrival counter is not back to zero
+extern "C" int mcb200_debug_check(mcb200_ctx* c, unsigned* bits_out) {
+    if (!c || !bits_out) return fail(MCB200_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    unsigned bits = 0;
+    if (c->check) CU(cudaMemcpy(&bits, c->check, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (guards_damaged()) bits |= 256u;
+    if (c->arrivals && c->arrivals_cap) {
+        std::vector<unsigned> h(c->arrivals_cap);
+        CU(cudaMemcpy(h.data(), c->arrivals, sizeof(unsigned) * c->arrivals_cap, cudaMemcpyDeviceToHost));
+        for (unsigned v : h) if (v != 0u) { bits |= 512u; break; }
+    }
+    *bits_out = bits;
+    return MCB200_OK;
+}
+#endif
 
 #ifdef MCB_TRACE
 extern "C" int mcb200_debug_set_trace(mcb200_ctx* c, unsigned long long* device_buf) {

@@ -77,6 +77,11 @@ struct SimArgs {
 #ifdef MCB_TRACE
     unsigned long long* trace;   // tools/kernel_timeline.py builds only: [n_warps][8] %globaltimer stamps (lane 0)
 #endif
+#ifdef MCB_CHECKED
+    unsigned* check;             // tools/checked_build.py builds only: OR of failed index checks (mcb200_debug_check)
+    unsigned long long slots_cap, xg_doubles;
+    long long pool_threads;
+#endif
     // Cross-GPU fused combine (trials-sharded operation without a collective): every GPU stores the finished moment
     // sums of an option into ITS row of an exchange buffer that lives on one GPU (peer memory over NVLink, mapped
     // through CUDA IPC) and bumps the option's cross-GPU arrival counter; the warp -- on whichever GPU -- that completes
@@ -236,6 +241,12 @@ __device__ __forceinline__ int owner_warp(long long r, long long R, long long W)
 #define MCB_LAZY_SLOT(payoff) ((payoff) == PAYOFF_GREEKS)
 #endif
 
+#ifdef MCB_CHECKED
+#define MCB_CHECK(cond, bit) do { if (!(cond)) atomicOr(a.check, (unsigned)(bit)); } while (0)
+#else
+#define MCB_CHECK(cond, bit) do { } while (0)
+#endif
+
 #ifdef MCB_TRACE
 #define MCB_STAMP(k) do { if (a.trace && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); \
                                                      a.trace[(size_t)w * 8 + (k)] = t_; } } while (0)
@@ -266,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
 
     Xoshiro256 g;
     const size_t gtid = (size_t)w * 32 + lane;              // the generator stream belongs to the LOGICAL thread
+    MCB_CHECK(STREAM != STREAM_FAST || (long long)gtid < a.pool_threads, 1);
     if (STREAM == STREAM_FAST) xoshiro_load(g, a.pool + 4ull * gtid);
 
     float creg[kConstInSmem ? 1 : kConst];
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
     MCB_STAMP(1);
 
     while (r < r_end) {
+        MCB_CHECK(o >= 0 && o < a.n_options && k >= 0 && k < a.rounds_per_option, 2);
         if (enter) {
             if (kConstInSmem) {
                 __syncwarp();
@@ -351,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
             solo = (w_first == w_last);
         }
         double* slot = a.slots + ((size_t)w + (size_t)o) * kAcc;
+        MCB_CHECK(((size_t)w + (size_t)o + 1) * kAcc <= a.slots_cap, 4);
         if (lane < kAcc) {
             if (!fresh) mine += slot[lane];                  // only this warp touches the slot before its arrival
             if (!kLazySlot || !(solo && segment_done)) slot[lane] = mine;
@@ -371,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                 unsigned prev = 0;
                 if (lane == 0) prev = atomicAdd(a.arrivals + o, 1u);
                 prev = __shfl_sync(0xffffffffu, prev, 0);
+                MCB_CHECK((int)prev <= w_last - w_first, 8);
                 complete = ((int)prev == w_last - w_first);
             }
             if (complete && !solo) {
@@ -382,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                 constexpr int kGroups = 32 / kAccPad;
                 const int i = lane % kAccPad, grp = lane / kAccPad;
                 const int n_seg = w_last - w_first + 1;
+                MCB_CHECK(((size_t)w_last + (size_t)o + 1) * kAcc <= a.slots_cap && w_first >= 0 && w_last < a.n_warps, 16);
                 s = 0.0;
                 if (i < kAcc) {
                     const double* base = a.slots + ((size_t)w_first + (size_t)o) * kAcc + i;
@@ -404,6 +420,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                 bool finish = a.finalize != 0;
                 if (a.xg_slots) {
                     // this GPU's share of option o is complete: publish it to the owner GPU, count the arrival there
+                    MCB_CHECK(((size_t)a.xg_rank * a.xg_n_max + (size_t)o + 1) * kAcc <= a.xg_doubles && o < a.xg_n_max, 32);
                     volatile double* row = a.xg_slots + ((size_t)a.xg_rank * a.xg_n_max + (size_t)o) * kAcc;
                     if (lane < kAcc) row[lane] = s;
                     __threadfence_system();
@@ -411,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
                     unsigned seen = 0;
                     if (lane == 0) seen = atomicAdd_system(a.xg_arrivals + o, 1u);
                     seen = __shfl_sync(0xffffffffu, seen, 0);
+                    MCB_CHECK((int)seen < a.xg_world, 32);
                     finish = finish && (int)seen == a.xg_world - 1;
                     if (finish) {
                         __threadfence_system();

@@ -38,6 +38,65 @@ def main():
     out = {"sm_count": info["sm_count"], "workloads": {}}
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
+    lib.mcb200_debug_set_trace(ctx._h, None)
+    # ---- floors: what an (almost) empty launch costs between two events on this box, for a kernel with ~100 bytes of
+    #      parameters (closed-form kernel, 1 option) and for simulate_kernel itself with next to no work (1 option x 8 trials)
+    def event_us(fn, reps=50):
+        iso = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            iso.append(1e3 * a.elapsed_time(b))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(200):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        period = 1e3 * a.elapsed_time(b) / 200
+        # primed: a ~40 us kernel (256 MiB fill) runs while the host enqueues event, launch, event -- the interval is
+        # then pure GPU-side time, the way bench.py's timed steps see it
+        primed = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            big.fill_(1)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            primed.append(1e3 * a.elapsed_time(b))
+        two = []
+        for _ in range(reps):                                        # two launches behind the primer: 2nd - 1st = period on the GPU
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            big.fill_(1); big.fill_(1)
+            a.record(); fn(); b.record(); fn(); c.record()
+            torch.cuda.synchronize()
+            two.append(1e3 * b.elapsed_time(c))
+        return {"isolated_us_median": float(np.median(iso)), "isolated_us_min": float(np.min(iso)),
+                "host_bound_back_to_back_period_us": period, "primed_gpu_side_us_median": float(np.median(primed)),
+                "primed_gpu_side_us_min": float(np.min(primed)), "primed_second_launch_us_median": float(np.median(two))}
+    big = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    one = [torch.full((1,), v, dtype=torch.float32, device=dev) for v in (100.0, 110.0, 0.25, 0.05, 0.5, 0.02)]
+    o10 = torch.zeros(10, 1, device=dev)
+    o4 = torch.zeros(4, 1, device=dev)
+    lib.mcb200_bs_batch_device.argtypes = None
+    N = pkg._native
+    def bs_launch():
+        N.check(lib.mcb200_bs_batch_device(ctx._h, 1, *[C.c_void_p(c.data_ptr()) for c in one],
+                                           N._VoidOut(*[o10[i].data_ptr() for i in range(10)]), C.c_void_p(st.cuda_stream)))
+    def tiny_sim():
+        ctx.price_batch_device(1, [c.data_ptr() for c in one], 2.0, 8.0, [o4[i].data_ptr() for i in range(4)], stream=st.cuda_stream)
+    def small_sim():
+        ctx.price_batch_device(1, [c.data_ptr() for c in one], 100.0, 1000.0, [o4[i].data_ptr() for i in range(4)], stream=st.cuda_stream)
+    out["floors"] = {"closed_form_kernel_1_option": event_us(bs_launch), "simulate_kernel_1_option_8_trials_2_steps": event_us(tiny_sim),
+                     "simulate_kernel_1_option_1000_trials_100_steps": event_us(small_sim)}
+    c1w = workload("c1")
+    c1cols = [torch.from_numpy(c).to(dev) for c in columns(c1w)]
+    c1out = torch.zeros(4, 112, device=dev)
+    def c1_sim():
+        ctx.price_batch_device(112, [c.data_ptr() for c in c1cols], 100.0, 1000.0, [c1out[i].data_ptr() for i in range(4)], stream=st.cuda_stream)
+    out["floors"]["simulate_kernel_c1"] = event_us(c1_sim)
+    print("floors", json.dumps(out["floors"]), flush=True)
     for name in names:
         w = workload(name)
         cols = [torch.from_numpy(c).to(dev) for c in columns(w)]
