@@ -42,6 +42,8 @@ def lib():
             fn = getattr(L, "ref_mc_" + name); fn.restype = _f; fn.argtypes = [_f] * 9 + [_u8p]
         L.ref_mc_pricing.restype = _f
         L.ref_mc_pricing.argtypes = [_f] * 9 + [_u8p, _dp, _dp, _fp, _fp]
+        L.ref_mc_set_conventions.restype = None
+        L.ref_mc_set_conventions.argtypes = [C.c_int, C.c_int]
         L.ref_mc_chunk_sums.restype = None
         L.ref_mc_chunk_sums.argtypes = [_u8p, C.c_int, _fp]
         L.ref_uniform_lane_stream.restype = None
@@ -127,6 +129,12 @@ def xoshiro_apply_poly(state, poly):
     pl = np.array(poly, dtype=np.uint64)
     lib().ref_xoshiro_apply_poly(st.ctypes.data_as(_u64p), pl.ctypes.data_as(_u64p))
     return st
+
+
+def set_conventions(seed_layout=0, uniform_mode=0):
+    """Switch the two simd_rand conventions the oracle has to assume (ref_mc.c): seed layout 0 = struct-of-arrays,
+    1 = array-of-structs; uniform mode 0 = (x >> 11) * 2^-53, 1 = exponent trick.  (0, 0) is the default everywhere."""
+    lib().ref_mc_set_conventions(int(seed_layout), int(uniform_mode))
 
 
 def uniform_lane_stream(seed256, lane, n):

@@ -35,10 +35,27 @@
 #define REF_LANES 8
 #define REF_SEED_BYTES 256
 
+/* The two conventions of simd_rand that cannot be read offline (see PARITY UNPINNED above) are switchable, so that
+ * vectors dumped from the real crate (tools/ref_vectors.rs -> tests/golden/ref_vectors.json) can falsify them in one
+ * run: tests/test_oracle.py::test_reference_vectors_when_present tries every combination and names the one that fits.
+ *   seed layout   0 (assumed): struct-of-arrays, state word k of lane l at byte 64*k + 8*l
+ *                 1          : array-of-structs, state word k of lane l at byte 32*l + 8*k
+ *   uniform mode  0 (assumed): (x >> 11) * 2^-53
+ *                 1          : the exponent trick, bits(0x3ff << 52 | x >> 12) - 1.0  (52 bits)               */
+static int g_seed_layout = 0, g_uniform_mode = 0;
+void ref_mc_set_conventions(int seed_layout, int uniform_mode) { g_seed_layout = seed_layout; g_uniform_mode = uniform_mode; }
+
 /* ---- rand32x8.rs:5-21 : one uniform per lane, u64 -> f64 in [0,1) -> f32 (round to nearest; may give 1.0f) ---- */
 static inline float ref_uniform_f32(xo256_t *lane) {
     const uint64_t x = xo256pp_next(lane);
-    const double d = (double)(x >> 11) * 0x1.0p-53;
+    double d;
+    if (g_uniform_mode == 0) {
+        d = (double)(x >> 11) * 0x1.0p-53;
+    } else {
+        const uint64_t b = (0x3ffULL << 52) | (x >> 12);
+        memcpy(&d, &b, 8);
+        d -= 1.0;
+    }
     return (float)d;
 }
 
@@ -53,7 +70,7 @@ static void ref_seed_chunk(const uint8_t *seed256, xo256_t lanes[REF_LANES]) {
     for (int k = 0; k < 4; k++)
         for (int l = 0; l < REF_LANES; l++) {
             uint64_t w;
-            memcpy(&w, seed256 + 64 * k + 8 * l, 8);   /* little-endian host */
+            memcpy(&w, seed256 + (g_seed_layout == 0 ? 64 * k + 8 * l : 32 * l + 8 * k), 8);   /* little-endian host */
             lanes[l].s[k] = w;
         }
 }
