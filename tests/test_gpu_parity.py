@@ -8,9 +8,13 @@ Bars (BASELINE.json north_star):
   * the reference's own tests (src/mc_simd.rs:781-907) replayed with their absolute tolerances.
 """
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
+
+from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -649,3 +653,24 @@ def test_c4_full_grid_greek_z_scores(ctx):
         assert abs(z.mean()) < (0.15 if "theta" in key else 0.10), (key, z.mean())
         assert 0.93 < z.std() < 1.07, (key, z.std())
         assert np.abs(z).max() < 5.0, (key, np.abs(z).max())
+
+
+def test_criterion_shape_driver(pkg):
+    """tools/criterion_shapes.py on two of the reference's criterion shapes (benches/benchmark.rs:32-44, :81-100) with a
+    reduced sample count: one batched call beats the 112 serial drop-ins of the reference's own bench loop, both agree
+    with the closed form, and the criterion-style statistics are well formed."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import criterion_shapes as cs
+    rows = cs.run(shapes=[(1000, 100, 15e-3, 419e-3), (20000, 100, 207e-3, 8.27)], samples=20, cpu_budget_s=1.5,
+                  scalar_budget_s=0.5)
+    assert [r["trials"] for r in rows] == [1000, 20000]
+    for r in rows:
+        assert r["batched"]["mean"] < 0.5 * r["serial"]["mean"], r          # 1 launch against 112 launch + sync round trips
+        assert r["batched"]["n"] == 20 and r["serial"]["n"] == 20 and r["cpu"]["n"] >= 1 and r["scalar"]["n"] >= 1
+        lo, hi = r["batched"]["ci95"]
+        assert lo <= r["batched"]["mean"] <= hi and sum(r["batched"]["outliers"].values()) <= 20
+        assert r["max_z_batched"] < 5.0 and r["max_z_serial"] < 6.5, r       # vs bs closed form, in batched-call SEs
+        assert r["cpu"]["mean"] > r["batched"]["mean"]                       # the CPU port never beats the batched GPU call
+    assert "| 1000 x 100 |" in cs.markdown(rows)
+    st = cs.criterion_stats([1.0] * 30 + [1.2, 2.0, 0.1])
+    assert st["outliers"]["high_severe"] >= 1 and st["outliers"]["low_severe"] >= 1 and st["n"] == 33
