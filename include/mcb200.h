@@ -12,8 +12,13 @@
  *
  * Reference quirks kept on purpose: steps and num_trials are f32; 8*floor(num_trials/8) paths
  * are simulated but the mean divides by num_trials (mc_simd.rs:49,77); 2*floor(steps/2) normals are consumed while
- * the drift uses steps (mc_simd.rs:44,47); vega and rho are per 1 point (/200h), theta per year; gamma and vega are
- * call-only.
+ * the drift uses steps (mc_simd.rs:44,47), so steps in (0,1) prices the deterministic forward; a negative num_trials is
+ * an empty chunk range and returns zeros (mc_simd.rs:49); vega and rho are per 1 point (/200h), theta per year; gamma
+ * and vega are call-only.
+ * Deviations: steps <= 0 (dt = T/steps is inf or NaN in the reference) is refused -- the drop-ins return NaN either
+ * way; the production stream draws the Box-Muller radius from a 23-bit uniform (largest single normal 5.65 sigma
+ * against ~8.6 sigma for the reference's 53-bit -> f32 uniforms) and the angle from an equispaced grid of 2^15
+ * directions; the reference-stream entry points of mcb200_testing.h consume the generator exactly like the reference.
  */
 #ifndef MCB200_H
 #define MCB200_H
@@ -27,7 +32,8 @@ typedef struct mcb200_ctx mcb200_ctx;
 
 typedef enum {
     MCB200_OK = 0,
-    MCB200_ERR_INVALID = 1,     /* bad argument: null pointer, n < 0, steps < 1, num_trials < 0, non-finite or > 2e9 */
+    MCB200_ERR_INVALID = 1,     /* bad argument: null pointer, n < 0, steps <= 0, non-finite or beyond +-2e9; a device-pointer
+                                   entry point on a multi-device context; xgpu launch / results out of turn */
     MCB200_ERR_CUDA = 2,        /* a CUDA runtime call failed; see mcb200_last_error() */
     MCB200_ERR_NO_DEVICE = 3,   /* no usable CUDA device (the library has no CPU path) */
     MCB200_ERR_NOMEM = 4
@@ -40,9 +46,20 @@ typedef enum {
 /* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per resident thread of
  * the price kernels: sm_count * ctas_per_sm * 256; the Greeks kernel uses the first grid_slots_greeks * 256 of them).
  * Thread slot i of the device uses substream jump^i(long_jump^substream_block(splitmix64(seed))): 2^128 draws per
- * thread, 2^64 thread slots per block, one block per GPU/rank (replaces per-chunk OS-entropy seeding,
- * mc_simd.rs:52-54).  Launches continue their substreams, so a fixed (seed, block, call sequence) is reproducible
- * bit for bit. */
+ * thread, up to 2^40 thread slots per block, one block per GPU/rank, reached in O(log block) polynomial applications
+ * (replaces per-chunk OS-entropy seeding, mc_simd.rs:52-54).  Launches continue their substreams.
+ *
+ * Reproducibility.  A fixed (seed, block, call sequence) reproduces every result bit for bit ON THE SAME GPU MODEL: the
+ * launch plan -- which thread simulates which path, and the order of the fixed-order sums -- is a function of the
+ * batch shape and of sm_count * ctas_per_sm (mcb200_plan_query), nothing else.  A GPU with a different SM count draws
+ * the same law from differently assigned substreams.
+ *
+ * Threads and streams.  Every entry point may be called from any thread (a mutex per context).  The pool, the partial-sum
+ * slots and the arrival counters are ONE set per context, so launches of one context never overlap on the device: a
+ * launch enqueued on a different stream than its predecessor first waits (cudaStreamWaitEvent, device side) for an
+ * event recorded behind the predecessor.  Two caller streams therefore interleave safely but do not run concurrently;
+ * use one context per stream (different substream blocks) for concurrency.  Stream handles passed to the *_device
+ * entry points must stay valid until the work enqueued on them has finished. */
 int mcb200_ctx_create(mcb200_ctx **ctx, int device, uint64_t seed, uint32_t substream_block);
 void mcb200_ctx_destroy(mcb200_ctx *ctx);
 int mcb200_ctx_set_seed(mcb200_ctx *ctx, uint64_t seed, uint32_t substream_block);
@@ -176,12 +193,18 @@ int mcb200_greeks_finalize_device(mcb200_ctx *ctx, int n, const float *risk_free
  *   all   : mcb200_price_xgpu_device(..., num_trials_local, flags, rank, total_paths, total_num_trials, stream)
  *   all   : mcb200_xgpu_results(ctx, n, call, put, call_se, put_se)  -- waits ON THE DEVICE (a one-thread kernel spinning
  *           on the buffer's epoch word) until the round is complete on every rank, then copies the results out.
- * Every rank must issue the same sequence of mcb200_price_xgpu_device calls (the round number is counted locally).
+ * Every rank must issue the same sequence of rounds (the round number is counted locally, after a successful launch).
+ * Launch and results ALTERNATE on every rank: a second mcb200_*_xgpu_device before the pending round's results were
+ * fetched returns MCB200_ERR_INVALID, so round k+1 can never mix with round k in the buffer.  Ranks of ONE process
+ * (one context per GPU, or several contexts on one GPU) share the owner's allocation with mcb200_xgpu_attach -- plain
+ * peer access, no IPC handle.  The device-side wait gives up after mcb200_xgpu_set_timeout seconds (default 120).
  * The kernel of mcb200_price_xgpu_device is enqueued on `cuda_stream`; the wait and the copy run on the context's
  * own stream behind an event recorded after that kernel. */
 #define MCB200_IPC_HANDLE_BYTES 64
 int mcb200_xgpu_create(mcb200_ctx *ctx, int n_max, int world, int greeks, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES]);
 int mcb200_xgpu_open(mcb200_ctx *ctx, const uint8_t handle[MCB200_IPC_HANDLE_BYTES], int n_max, int world, int greeks);
+int mcb200_xgpu_attach(mcb200_ctx *ctx, mcb200_ctx *owner, int n_max, int world, int greeks);
+int mcb200_xgpu_set_timeout(mcb200_ctx *ctx, double seconds);
 int mcb200_xgpu_close(mcb200_ctx *ctx);
 int mcb200_price_xgpu_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
                              const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
@@ -206,40 +229,6 @@ int mcb200_bs_batch(mcb200_ctx *ctx, int n, const float *spot, const float *stri
 int mcb200_bs_batch_device(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
                            const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
                            float *const out[MCB200_N_GREEK_OUTPUTS], void *cuda_stream);
-
-/* ------------------------------------------------------------------ parity / inspection ------------------------ */
-/* Reference-stream mode: consume the generator exactly like the reference (a 256-byte simd_rand seed per 8-path
- * chunk, two 64-bit outputs per Box-Muller pair, 53-bit -> f64 -> f32 uniforms; rand32x8.rs:5-21, mc_simd.rs:9-21).
- * chunk_seeds: n * floor(num_trials/8) * 256 bytes (host).  growth_out (host, nullable): n * 8*floor(num_trials/8)
- * per-path terminal growth factors S_T / spot.  Test-only: this is the one mode that writes path data to HBM. */
-int mcb200_price_batch_refstream(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
-                                 const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
-                                 const float *dividend_yield, float steps, float num_trials, unsigned flags,
-                                 const uint8_t *chunk_seeds, float *call_out, float *put_out, float *call_se,
-                                 float *put_se, float *growth_out);
-int mcb200_greeks_batch_refstream(mcb200_ctx *ctx, int n, const float *spot, const float *strike,
-                                  const float *volatility, const float *risk_free_rate, const float *years_to_expiry,
-                                  const float *dividend_yield, float steps, float num_trials,
-                                  const mcb200_bumps *bumps, const uint8_t *chunk_seeds,
-                                  float *const out[MCB200_N_GREEK_OUTPUTS], float *const out_se[MCB200_N_GREEK_OUTPUTS]);
-/* Production stream with the per-path growth factors dumped (test-only).  growth_out: n * n_paths floats (host). */
-int mcb200_price_batch_dump(mcb200_ctx *ctx, int n, const float *spot, const float *strike, const float *volatility,
-                            const float *risk_free_rate, const float *years_to_expiry, const float *dividend_yield,
-                            float steps, float num_trials, unsigned flags,
-                            float *call_out, float *put_out, float *call_se, float *put_se, float *growth_out);
-/* Copy generator states [first, first+count) of the pool to the host (4 x u64 per thread slot). */
-int mcb200_ctx_export_states(mcb200_ctx *ctx, int64_t first, int64_t count, uint64_t *states_out);
-
-/* Kernel timing for roofline accounting: when enabled, CUDA events are recorded on the launch stream immediately
- * before and after every simulate-kernel launch; mcb200_ctx_last_sim_ms() waits for the latest one and returns its
- * device duration in milliseconds (the fused path + reduction + finalisation kernel, the only kernel of a batch). */
-int mcb200_ctx_set_timing(mcb200_ctx *ctx, int enabled);
-int mcb200_ctx_last_sim_ms(mcb200_ctx *ctx, float *ms_out);
-
-/* Pipe-throughput microbenchmarks (MUFU / FMA / ALU / issue) that fix the roofline denominator with measured numbers.
- * Writes up to `cap` results; returns the number written (negative = error). */
-typedef struct { char name[32]; double ops_per_clk_per_sm; double elapsed_ms; double sm_clock_mhz; } mcb200_pipe_rate;
-int mcb200_microbench(mcb200_ctx *ctx, mcb200_pipe_rate *out, int cap);
 
 /* ------------------------------------------------------------------ the 12 drop-ins ---------------------------- */
 /* Same names, parameter lists and semantics as /root/reference/src/mc_simd.rs:477-779.  They run on a lazily
@@ -270,7 +259,9 @@ float mc_simd_call_theta(float spot, float strike, float volatility, float risk_
 float mc_simd_put_theta(float spot, float strike, float volatility, float risk_free_rate, float years_to_expiry,
                         float delta_years_to_expiry, float dividend_yield, float steps, float num_trials);  /* :755-779 */
 
-/* Select / inspect the default context used by the drop-ins (NULL restores lazy creation). */
+/* Select / inspect the default context used by the drop-ins.  MCB200_DEVICES=0,1,.. makes it a multi-device context.
+ * The pointer returned by mcb200_default_ctx is borrowed: valid until the next mcb200_default_ctx_reset (a drop-in
+ * running on another thread keeps the old context alive until it returns). */
 int mcb200_default_ctx(mcb200_ctx **out);
 int mcb200_default_ctx_reset(int device, uint64_t seed, uint32_t substream_block);
 

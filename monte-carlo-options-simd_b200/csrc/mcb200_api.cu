@@ -18,6 +18,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/mcb200.h"
+#include "../../include/mcb200_testing.h"
 #include "../../include/xoshiro256_jump_tables.h"
 #include "mcb200_kernels.cuh"
 #include "mcb200_plan.h"
@@ -234,13 +235,21 @@ static int seed_pool(mcb200_ctx* c) {
 }
 
 // Called with the context mutex held, before / after enqueuing work that touches the context's shared device state.
+// A launch on a CALLER stream records the event right away (the caller may destroy that stream at any time); a launch
+// on the context's own stream records nothing -- the event is recorded on that stream lazily, at the moment a launch
+// arrives on a different stream -- so the host-buffer entry points and the drop-ins pay no event per call.
 static int order_before(mcb200_ctx* c, cudaStream_t st) {
-    if (c->order_valid && c->order_stream != st) CU(cudaStreamWaitEvent(st, c->order_ev, 0));
+    if (!c->order_valid || c->order_stream == st) return MCB200_OK;
+    if (!c->order_ev) CU(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+    if (c->order_stream == c->stream) CU(cudaEventRecord(c->order_ev, c->stream));     // lazy record for the own stream
+    CU(cudaStreamWaitEvent(st, c->order_ev, 0));
     return MCB200_OK;
 }
 static int order_after(mcb200_ctx* c, cudaStream_t st) {
-    if (!c->order_ev) CU(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(c->order_ev, st));
+    if (st != c->stream) {
+        if (!c->order_ev) CU(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(c->order_ev, st));
+    }
     c->order_stream = st; c->order_valid = true;
     return MCB200_OK;
 }

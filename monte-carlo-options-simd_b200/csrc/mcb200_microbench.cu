@@ -9,7 +9,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../../include/mcb200.h"
+#include "../../include/mcb200_testing.h"
 #include "mcb200_pair.cuh"
 
 namespace mcb200 {
