@@ -112,7 +112,8 @@ int mcb200_ctx_child(mcb200_ctx *ctx, int i, mcb200_ctx **child);  /* borrowed p
 /* How one batch is split over n_shards GPUs -- the same policy for the multi-device context (shard = device index) and
  * for one-process-per-GPU operation (shard = rank).  Pure host logic.
  *   MCB200_SHARD_SINGLE   the batch does not fill one GPU (or n_shards == 1): shard 0 runs all of it;
- *   MCB200_SHARD_OPTIONS  n_options >= 16 * n_shards: shard s owns options [s*n/S, (s+1)*n/S), no exchange step;
+ *   MCB200_SHARD_OPTIONS  n_options >= n_shards and ceil(n/S) within 10 % of n/S (always so for n >= 10 S): shard s owns
+ *                         options [s*n/S, (s+1)*n/S), no exchange step;
  *   MCB200_SHARD_TRIALS   otherwise: shard s simulates chunks [s*C/S, (s+1)*C/S) of the C = floor(num_trials/8) 8-path
  *                         chunks of EVERY option; per-option fp64 moment sums are added in shard order and finalised
  *                         once with total_paths and the caller's num_trials (the divisor of mc_simd.rs:77). */

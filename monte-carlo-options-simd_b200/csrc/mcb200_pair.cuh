@@ -19,14 +19,15 @@ constexpr int kWarps = kThreads / 32;
 // profiles/r2_microbench_tri_vs_quad.json), so low occupancy costs nothing and buys register-resident accumulators.
 // Measured with tools/ab_flags.sh (profiles/r2_ab_kernel_variants.txt), roofline.frac on C2 / C3 / C5R / C4:
 //   price / antithetic kernels: 4 CTAs/SM (64 registers); 2 -> 0.856 / 0.865 / 1.022, 4 -> 0.877 / 0.890 / 1.057,
-//                               8 tris per iteration -> 0.895 / 0.912 / 1.080 (5 CTAs/SM: 0.835 / 0.690 / 1.009)
+//                               8 -> 0.895 / 0.912 / 1.080, 16 tris per iteration -> 0.913 / 0.930 / 1.082
+//                               (5 CTAs/SM: 0.835 / 0.690 / 1.009)
 //   Greeks kernel (20 moment registers): 3 CTAs/SM; 4 tris per iteration -> C4 1.024, 6 -> 1.043, 8 -> 1.035
 // The MCB_* macros exist for that sweep only (MCB200_NVCC_FLAGS in build.py).
 #ifndef MCB_PRICE_CTAS
 #define MCB_PRICE_CTAS 4
 #endif
 #ifndef MCB_PRICE_UNROLL
-#define MCB_PRICE_UNROLL 8
+#define MCB_PRICE_UNROLL 16
 #endif
 #ifndef MCB_GREEKS_CTAS
 #define MCB_GREEKS_CTAS 3

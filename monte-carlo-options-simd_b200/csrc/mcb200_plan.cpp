@@ -48,7 +48,8 @@ int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb2
 // Sharding policy of a batch over `n_shards` GPUs (one process with several devices, or one process per GPU): replaces
 // the reference's single fan-out over a thread pool (mc_simd.rs:49-51) and its reduce (mc_simd.rs:71-74) at node scale.
 //   single         the batch does not fill one GPU (rounds <= its resident warps), or one shard: shard 0 runs it alone;
-//   options-major  n >= 16 * n_shards: contiguous blocks of options, no exchange (imbalance <= 1/16);
+//   options-major  n >= n_shards and the largest block is within 10 % of the mean (always true for n >= 10 * n_shards):
+//                  contiguous blocks of options, no exchange step;
 //   trials-minor   otherwise: every shard simulates a contiguous range of the 8-path chunks of ALL options; the fp64
 //                  moment sums are added in shard order and finalised once.
 int make_shard(int n_options, float steps, float num_trials, int n_shards, int shard, int grid_slots, mcb200_shard* out) {
@@ -64,7 +65,8 @@ int make_shard(int n_options, float steps, float num_trials, int n_shards, int s
     if (n_shards == 1 || n_options == 0 || chunks == 0 || whole.total_rounds <= resident) {
         s.mode = MCB200_SHARD_SINGLE;
         if (shard == 0) { s.option_begin = 0; s.option_end = n_options; s.num_trials_local = num_trials; s.active = 1; }
-    } else if ((long long)n_options >= 16ll * n_shards) {
+    } else if (n_options >= n_shards &&
+               10ll * (((long long)n_options + n_shards - 1) / n_shards) * n_shards <= 11ll * n_options) {
         s.mode = MCB200_SHARD_OPTIONS;
         s.option_begin = (int)((long long)shard * n_options / n_shards);
         s.option_end = (int)(((long long)shard + 1) * n_options / n_shards);

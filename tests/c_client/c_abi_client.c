@@ -16,7 +16,7 @@ int main(int argc, char **argv) {
     if (mcb200_plan_query(1, 0.0f, 1000.0f, 592, &p) != MCB200_ERR_INVALID) return 13;
 
     mcb200_shard sh;                                                /* 8 GPUs: few options -> trials-minor; a sweep -> options-major */
-    if (mcb200_shard_query(8, 100.0f, 8e6f, 8, 3, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_TRIALS ||
+    if (mcb200_shard_query(5, 100.0f, 8e6f, 8, 3, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_TRIALS ||
         sh.num_trials_local != 1e6f || sh.total_paths != 8e6) return 14;
     if (mcb200_shard_query(100000, 252.0f, 1e4f, 8, 7, 592, &sh) != MCB200_OK || sh.mode != MCB200_SHARD_OPTIONS ||
         sh.option_begin != 87500 || sh.option_end != 100000) return 15;

@@ -118,13 +118,14 @@ def test_planner_rejects_bad_requests(pkg):
 
 
 def test_shard_policy(pkg):
-    """mcb200_shard_query: single device when the batch does not fill one GPU, options-major blocks for >= 16 options per
-    GPU, trials-minor chunk ranges otherwise; the shards tile the batch exactly once."""
+    """mcb200_shard_query: single device when the batch does not fill one GPU, options-major blocks when they balance to
+    within 10 %, trials-minor chunk ranges otherwise; the shards tile the batch exactly once."""
     slots = 592
     for n, steps, trials, world, mode in [(112, 100.0, 1000.0, 8, "single"), (1, 100.0, 1000.0, 4, "single"),
-                                          (112, 100.0, 20000.0, 8, "trials"), (112, 100.0, 20000.0, 2, "options"),
+                                          (112, 100.0, 20000.0, 8, "options"), (112, 100.0, 20000.0, 2, "options"),
+                                          (20, 100.0, 1e6, 8, "trials"), (100, 100.0, 1e5, 8, "options"), (8, 100.0, 8e6, 8, "options"),
                                           (100000, 252.0, 1e4, 8, "options"), (100000, 252.0, 1e6, 7, "options"),
-                                          (8, 100.0, 8e6, 8, "trials"), (4096, 252.0, 1e5, 8, "options"),
+                                          (5, 100.0, 8e6, 8, "trials"), (4096, 252.0, 1e5, 8, "options"),
                                           (5, 50.0, 1000003.0, 3, "trials"), (100, 10.0, 1e6, 1, "single")]:
         shards = [pkg.shard_query(n, steps, trials, world, r, slots) for r in range(world)]
         assert all(s["mode"] == mode for s in shards), (n, trials, world, shards[0]["mode"])

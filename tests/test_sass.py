@@ -58,7 +58,7 @@ def test_all_kernel_variants_are_in_the_library(funcs):
         assert k in names
 
 
-@pytest.mark.parametrize("payoff,pairs_per_iter", [(0, 24), (1, 24), (2, 18)])
+@pytest.mark.parametrize("payoff,pairs_per_iter", [(0, 48), (1, 48), (2, 18)])
 def test_tri_loop_instruction_mix(funcs, payoff, pairs_per_iter):
     """tri_fast loop of the production (STREAM_FAST) kernels: 3 MUFU and <= 22.25 instructions per Box-Muller pair, of
     which <= 12.85 on the ALU pipe (LOP3 / SHF / IADD3 / LEA / PRMT + the loop counter); every carry add and every

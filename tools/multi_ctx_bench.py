@@ -4,7 +4,7 @@ step, the library splits the batch over D GPUs (mcb200_shard_query policy), D = 
 
     python tools/multi_ctx_bench.py [--workloads c5r c4 c2 few] [--reps 10]      (gpurun --gpus 8)
 
-"few" = 8 options x 8e6 trials x 100 steps: the trials-minor split (per-device moment sums, host sum in device order, one
+"few" = 5 options x 8e6 trials x 100 steps: the trials-minor split (per-device moment sums, host sum in device order, one
 finalisation).  Wall clock around `reps` calls after 3 warm-up calls; host buffers in and out inside the timed region.
 """
 import argparse
@@ -32,7 +32,7 @@ def main():
     out = {"gpus_present": n_gpu, "results": []}
     for name in args.workloads:
         if name == "few":
-            w = dict(key="few", name="8 options x 8e6 trials x 100 steps (trials-minor)", spots=np.linspace(90, 125, 8).astype(np.float32),
+            w = dict(key="few", name="5 options x 8e6 trials x 100 steps (trials-minor)", spots=np.linspace(90, 130, 5).astype(np.float32),
                      strikes=None, steps=100.0, trials=8e6, kind="price", av=False)
         else:
             w = workload(name)
