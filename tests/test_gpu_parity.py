@@ -58,6 +58,31 @@ def test_pool_states_are_jump_substreams(ctx, oracle, xoshiro_kat):
     got = ctx.export_states(4096 + 8 + 1, 1)[0]
     assert [int(v) for v in got] == [int(v) for v in far]
 
+    def slot_state(i):
+        st = base
+        for k in range(40):
+            if (i >> k) & 1:
+                st = oracle.xoshiro_apply_poly(st, table[k])
+        return [int(v) for v in st]
+    # the END of the pool (the last resident thread of the price kernels), the last slot the Greeks kernel uses and the
+    # first one it does not, and random slots in between: all 2^k polynomials up to the pool size get exercised
+    info = ctx.info()
+    last = info["pool_threads"] - 1
+    greeks_last = info["grid_slots_greeks"] * info["threads_per_cta"] - 1
+    rng = np.random.default_rng(5)
+    probes = [last, last - 1, greeks_last, greeks_last + 1, 65535, 65536] + [int(v) for v in rng.integers(0, last, 24)]
+    for i in probes:
+        assert [int(v) for v in ctx.export_states(i, 1)[0]] == slot_state(i), i
+    # every state of the pool is distinct and non-zero (a zero state would be a fixed point of the generator)
+    whole = ctx.export_states(0, info["pool_threads"])
+    assert len(np.unique(whole, axis=0)) == info["pool_threads"] and np.all(whole.any(axis=1))
+    # a large substream block reaches its state in O(log block) polynomial applications (it used to be O(block))
+    import time
+    t0 = time.perf_counter()
+    with type(ctx)(device=0, seed=SEED, substream_block=0xF00DF00D) as far_block:
+        assert far_block.info()["substream_block"] == 0xF00DF00D
+    assert time.perf_counter() - t0 < 20.0
+
 
 def test_substream_blocks_use_long_jump(pkg, oracle, xoshiro_kat):
     ljump = [int(x) for x in xoshiro_kat["long_jump_poly"]]
@@ -117,8 +142,9 @@ def test_reference_stream_antithetic_and_greeks_match_oracle(ctx, oracle):
 
 
 def test_production_stream_per_path_parity(pkg, oracle):
-    """Production convention (one 64-bit draw per Box-Muller pair, per-thread substreams): every path reproduced by
-    the CPU model from the exported generator states and the launch plan (mcb200_plan / mcb200_plan_warp_range)."""
+    """Production convention (two 64-bit draws per three Box-Muller pairs, left-over pairs one draw each, per-thread
+    substreams): every path reproduced by the CPU model (oracle/fast_model.c) from the exported generator states and
+    the launch plan (mcb200_plan / mcb200_plan_warp_range)."""
     with pkg.Context(device=0, seed=4242) as c:
         spots = (90.0 + np.arange(41)).astype(np.float32)
         steps, trials = 252.0, 8008.0                      # 8008 paths = 250.25 rounds: the last round is ragged,
@@ -156,6 +182,42 @@ def test_production_stream_per_path_parity(pkg, oracle):
             pay = np.maximum(np.float64(s) * got["growth"][o].astype(np.float64) - GRID["strike"], 0.0)
             want = pay.sum() / trials * math.exp(-GRID["r"] * GRID["t"])
             assert got["call"][o] == pytest.approx(want, rel=1e-5)
+
+
+def test_every_pool_substream_is_independent_on_the_device(pkg):
+    """One option spread over EVERY resident thread (4 rounds per warp), 6 steps = one triple per path, per-path sums
+    recovered from the dumped growth factors: unit variance per term, no correlation between consecutive paths of one
+    thread (serial), between neighbouring lanes, between neighbouring warps, between the first and the last warp of the
+    pool, nor in the squares -- over all 151 552 substreams of the pool, its last slots included."""
+    with pkg.Context(device=0, seed=99) as c:
+        info = c.info()
+        warps = info["grid_slots"] * 8
+        n_paths = warps * 4 * 32
+        plan = c.plan(1, 6.0, float(n_paths))
+        assert plan["warps"] == warps and plan["max_rounds_per_warp"] == 4 and plan["half_steps"] == 3
+        vol, t = 0.3, 1.0
+        got = c.price_batch_dump([100.0], 100.0, vol, 0.0, t, 0.0, 6.0, float(n_paths))
+    dt = t / 6.0
+    drift = 6.0 * (-0.5 * vol * vol) * dt
+    z = (np.log(got["growth"][0].astype(np.float64)) - drift) / (vol * math.sqrt(dt))      # sum of 6 unit normals
+    m = z.reshape(warps, 4, 32)                                                            # [warp][round][lane]
+    n = m.size
+    assert abs(z.mean()) < 4.5 * math.sqrt(6.0 / n) and abs(z.var() / 6.0 - 1.0) < 4.5 * math.sqrt(2.0 / n)
+    assert abs(((z / math.sqrt(6.0)) ** 4).mean() - 3.0) < 0.03                            # gaussian kurtosis
+
+    def corr(a, b):
+        a, b = a.ravel() - a.mean(), b.ravel() - b.mean()
+        return float((a * b).mean() / math.sqrt((a * a).mean() * (b * b).mean()))
+    tol = lambda k: 4.5 / math.sqrt(k)
+    assert abs(corr(m[:, :-1, :], m[:, 1:, :])) < tol(n * 3 // 4)                         # serial, same thread
+    assert abs(corr(m[:, :, :-1], m[:, :, 1:])) < tol(n * 31 // 32)                       # neighbouring lanes
+    assert abs(corr(m[:-1], m[1:])) < tol(n)                                               # neighbouring warps
+    assert abs(corr(m[:64], m[-64:])) < tol(64 * 128)                                      # both ends of the pool
+    assert abs(corr(m[:, :-1, :] ** 2, m[:, 1:, :] ** 2)) < tol(n * 3 // 4)
+    assert abs(corr(m[:, :, :-1] ** 2, m[:, :, 1:] ** 2)) < tol(n * 31 // 32)
+    # per-thread means over the 4 paths of each thread: no thread is an outlier beyond what 151 552 normals allow
+    per_thread = m.mean(axis=1).ravel() / math.sqrt(6.0 / 4.0)
+    assert np.abs(per_thread).max() < 5.6
 
 
 # ---------------------------------------------------------------------------------------------- reference tests replayed

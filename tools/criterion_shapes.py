@@ -125,7 +125,7 @@ def markdown(rows):
         return "%s [%s, %s]%s" % (fmt_time(st["mean"]), fmt_time(st["ci95"][0]), fmt_time(st["ci95"][1]),
                                   " (n=%d, %d outl.)" % (st["n"], n_out) if st["n"] > 1 else " (n=1)")
     lines = ["| trials x steps | M1 `mc` / `mc_simd` (README) | scalar port, 1 thread | CPU port (%d thr) | B200, 112 serial drop-ins | "
-             "B200, one batched call | batched path-steps/s | max z (batched / serial) |" % rows[0]["cpu_threads"],
+             "B200, one batched call | batched path-steps/s | max z near the money (batched / serial) |" % rows[0]["cpu_threads"],
              "|---|---|---|---|---|---|---|---|"]
     for r in rows:
         lines.append("| %d x %d | %s / %s | %s | %s | %s | %s | %.3g | %.1f / %.1f |" % (
@@ -142,8 +142,9 @@ def main():
     ap.add_argument("--samples", type=int, default=100)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "criterion_shapes"))
     ap.add_argument("--write-baseline", action="store_true")
+    ap.add_argument("--from-json", default=None, help="format rows measured earlier (no GPU needed) instead of measuring")
     args = ap.parse_args()
-    rows = run(samples=args.samples)
+    rows = json.load(open(args.from_json)) if args.from_json else run(samples=args.samples)
     md = markdown(rows)
     print(md)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
