@@ -70,7 +70,7 @@ def test_multi_device_context_on_two_real_gpus():
     spots = np.linspace(70, 150, 64).astype(np.float32)
     with pkg.Context(devices=[0, 1], seed=31) as multi:
         got = multi.price_batch(spots, *G, 100.0, 80000.0)
-        few = multi.price_batch(spots[:4], *G, 100.0, 800000.0)
+        few = multi.price_batch(spots[:5], *G, 100.0, 800000.0)      # 5 options on 2 GPUs: trials-minor
         bs = multi.bs_batch(spots, *G)
     for d, (lo, hi) in enumerate(((0, 32), (32, 64))):
         with pkg.Context(device=d, seed=31, substream_block=d) as one:
@@ -82,22 +82,22 @@ def test_multi_device_context_on_two_real_gpus():
     moms = []
     for d in (0, 1):
         dev = torch.device("cuda", d)
-        cols = [torch.tensor(spots[:4], device=dev)] + [torch.full((4,), v, dtype=torch.float32, device=dev) for v in G]
+        cols = [torch.tensor(spots[:5], device=dev)] + [torch.full((5,), v, dtype=torch.float32, device=dev) for v in G]
         with pkg.Context(device=d, seed=31, substream_block=d) as one:
             with torch.cuda.device(dev):
                 # advance the substreams exactly like the multi context did (one options-major batch of 32 options)
                 one.price_batch(spots[32 * d:32 * d + 32], *G, 100.0, 80000.0)
-                m = torch.zeros(4, 4, dtype=torch.float64, device=dev)
-                one.price_moments_device(4, [c.data_ptr() for c in cols], 100.0, 400000.0, m.data_ptr())
+                m = torch.zeros(5, 4, dtype=torch.float64, device=dev)
+                one.price_moments_device(5, [c.data_ptr() for c in cols], 100.0, 400000.0, m.data_ptr())
                 torch.cuda.synchronize(dev)
                 moms.append(m.cpu())
     total = (moms[0] + moms[1]).cuda(0)
     dev0 = torch.device("cuda", 0)
-    rate = torch.full((4,), GRID["r"], dtype=torch.float32, device=dev0)
-    years = torch.full((4,), GRID["t"], dtype=torch.float32, device=dev0)
-    vals = torch.zeros(4, 4, device=dev0)
+    rate = torch.full((5,), GRID["r"], dtype=torch.float32, device=dev0)
+    years = torch.full((5,), GRID["t"], dtype=torch.float32, device=dev0)
+    vals = torch.zeros(4, 5, device=dev0)
     with pkg.Context(device=0, seed=1) as fin:
-        fin.price_finalize_device(4, rate.data_ptr(), years.data_ptr(), total.data_ptr(), 800000.0, 800000.0,
+        fin.price_finalize_device(5, rate.data_ptr(), years.data_ptr(), total.data_ptr(), 800000.0, 800000.0,
                                   [vals[i].data_ptr() for i in range(4)])
         torch.cuda.synchronize(dev0)
     for i, k in enumerate(("call", "put", "call_se", "put_se")):
