@@ -11,7 +11,7 @@ is timed once as a sub-record).  One JSON line is printed by rank 0.
 
   N = 1     value / roofline / e2e on the default workload, plus `sub` records (their own roofline each) for C1, C2, C3
             (price kernels on the reference's own 112-spot grid), C4 (the fused-Greeks kernel), the reference-stream
-            parity kernel on C2 and one full-size C5 step.
+            parity kernel on C2 and one full-size C5 step (`sub.c5_full`, also reported at every N > 1).
   N > 1     STRONG scaling of the same one batch: the library's shard policy (mcb200_shard_query) gives every rank
             its options-major block (or trials-minor range); every timed step ends with the exchange the split needs
             -- results gathered to rank 0 over NCCL (options-major), or the moment sums all-reduced and finalised
@@ -555,9 +555,11 @@ def b200_arm(args, w):
                 r["vs_readme_m1_derived"] = r["value"] / README_M1_DERIVED[key]
             subs[key] = r
         subs["c2_refstream"] = b.refstream_record(workload("c2"), 5)
-        if args.full_c5 and w["key"] != "c5":
-            subs["c5_full"] = b.measure(workload("c5"), 1, 1, 0.0, sample_clocks=False)
-            subs["c5_full"]["note"] = "full-size config 5 on one GPU: one warm-up step and one timed step (10.6 s each)"
+    if args.full_c5 and not args.no_subs and w["key"] != "c5":
+        # the configuration the metric's "sharded over 2/4/8 B200" wording belongs to, at FULL size, at every N: one
+        # warm-up step and one timed step (10 s each on one GPU, 1.25 s on eight), same shard policy and exchange
+        subs["c5_full"] = b.measure(workload("c5"), 1, 1, 0.0, sample_clocks=False)
+        subs["c5_full"]["note"] = "full-size config 5 (1e5 pairs x 1e6 trials x 252 steps): one warm-up step and one timed step"
     if b.rank == 0:
         clocks = b.sampler.summary()
         cpu = None
@@ -604,7 +606,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-subs", action="store_true", help="skip the C1-C4 / refstream / full-C5 sub-records (N = 1)")
-    ap.add_argument("--full-c5", type=int, default=1, help="time one full-size C5 step as a sub-record (N = 1; ~25 s)")
+    ap.add_argument("--full-c5", type=int, default=1, help="time one full-size C5 step as a sub-record (~50 s / N)")
     ap.add_argument("--roof-seconds", type=float, default=1.0,
                     help="minimum duration of the kernel-only roofline pass (clock sampling needs ~1 s)")
     args = ap.parse_args()

@@ -40,8 +40,14 @@ def _worker(rank, world, port, out_path):
     pkg = load_package()
     from oracle import oracle
     sh = pkg.sharding
-    local, total_paths = sh.partition_trials(PARAMS["trials"], world, rank)
-    first_chunk = sum(sh.partition_trials(PARAMS["trials"], world, r)[0] for r in range(rank)) // 8
+    # the rank's share comes from the LIBRARY's shard policy (mcb200_shard_query, pure host logic): 3 options on 2 ranks
+    # with a batch larger than one (here: tiny, 2-CTA) GPU -> trials-minor
+    shard = pkg.shard_query(len(SPOTS), PARAMS["steps"], PARAMS["trials"], world, rank, 2)
+    assert shard["mode"] == "trials" and shard["active"]
+    local, total_paths = int(shard["num_trials_local"]), int(shard["total_paths"])
+    assert (local, total_paths) == sh.partition_trials(PARAMS["trials"], world, rank)
+    first_chunk = sum(int(pkg.shard_query(len(SPOTS), PARAMS["steps"], PARAMS["trials"], world, r, 2)["num_trials_local"])
+                      for r in range(rank)) // 8
     all_seeds = oracle.chunk_seeds(int(PARAMS["trials"]) // 8, 4321).reshape(-1, 256)
     mine = np.ascontiguousarray(all_seeds[first_chunk:first_chunk + local // 8])
     m = torch.tensor([_moments(oracle, s, mine, float(local)) for s in SPOTS], dtype=torch.float64)
@@ -77,3 +83,44 @@ def test_trials_sharding_world2_gloo(tmp_path, oracle, pkg):
         var = (whole[1] - whole[0] ** 2 / n) / (n - 1)
         assert got["call_se"][i] == pytest.approx(math.sqrt(var / n) * n / PARAMS["trials"] * disc, rel=1e-5)
     assert list(got["block"]) == [0, 1]                                      # options-major block of rank 0 of 2: [0*3//2, 1*3//2)
+
+
+def _options_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = load_package()
+    from oracle import oracle
+    spots = np.linspace(80.0, 140.0, 40).astype(np.float32)
+    shard = pkg.shard_query(len(spots), PARAMS["steps"], 800.0, world, rank, 2)      # 40 options, 2 ranks: options-major
+    lo, hi = shard["option_begin"], shard["option_end"]
+    mine = torch.zeros(len(spots) // world, dtype=torch.float32)
+    for j, o in enumerate(range(lo, hi)):                  # seeds follow the OPTION, so the split cannot change a result
+        seeds = oracle.chunk_seeds(100, 1000 + o)
+        mine[j] = oracle.pricing_detail(float(spots[o]), PARAMS["strike"], PARAMS["vol"], PARAMS["r"], PARAMS["t"],
+                                        PARAMS["q"], PARAMS["steps"], 800.0, 1.0, seeds)["price"]
+    parts = [torch.zeros_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)                        # the exchange step of the options-major split (NCCL on GPUs)
+    if rank == 0:
+        np.savez(out_path, prices=torch.cat(parts).numpy(), mode=np.array([shard["mode"] == "options"]),
+                 block=np.array([lo, hi]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_options_sharding_world2_gloo(tmp_path, oracle, pkg):
+    """Options-major split on two ranks: contiguous blocks from mcb200_shard_query, results gathered to rank 0, equal to
+    the unsharded loop option by option."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "opt.npz")
+    mp.spawn(_options_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert bool(got["mode"][0]) and list(got["block"]) == [0, 20]
+    spots = np.linspace(80.0, 140.0, 40).astype(np.float32)
+    for o, s in enumerate(spots):
+        want = oracle.pricing_detail(float(s), PARAMS["strike"], PARAMS["vol"], PARAMS["r"], PARAMS["t"], PARAMS["q"],
+                                     PARAMS["steps"], 800.0, 1.0, oracle.chunk_seeds(100, 1000 + o))["price"]
+        assert got["prices"][o] == np.float32(want), o
