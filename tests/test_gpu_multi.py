@@ -243,3 +243,63 @@ def test_two_caller_streams_on_one_context_serialise(pkg):
     for i, (x, y) in enumerate(zip(two, one)):
         assert np.array_equal(x, y), i
         assert np.all(np.isfinite(x)) and np.all(x[2] > 0)
+
+
+def test_dropins_survive_a_concurrent_default_context_reset(pkg):
+    """The drop-ins hold a reference to the default context for the duration of a call: resetting it from another thread
+    (which used to free the context under the callers' feet) neither crashes nor produces a non-finite price."""
+    import threading
+    pkg.mc_simd.reset_default_context(device=0, seed=1)
+    stop, errors, results = threading.Event(), [], []
+
+    def caller():
+        try:
+            while not stop.is_set():
+                v = pkg.mc_simd.call_price(100.0, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 4000.0)
+                g = pkg.mc_simd.gamma(100.0, 0.01, 110.0, 0.25, 0.05, 0.5, 0.02, 100.0, 4000.0)
+                results.append((v, g))
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+    threads = [threading.Thread(target=caller) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for i in range(25):
+        pkg.mc_simd.reset_default_context(device=0, seed=100 + i)
+    stop.set()
+    for t in threads:
+        t.join()
+    assert not errors and len(results) > 20
+    v = np.array(results)
+    assert np.all(np.isfinite(v)) and np.all(np.abs(v[:, 0] - 3.86) < 1.5) and np.all(v[:, 1] >= 0.0)
+
+
+def test_multi_device_context_from_several_host_threads(pkg):
+    """Batches submitted to ONE multi-device context from several host threads are serialised by the library: every
+    result is finite and statistically right, and the context is still bit-reproducible afterwards."""
+    import threading
+    spots = np.linspace(80, 140, 64).astype(np.float32)
+    with pkg.Context(devices=[0, 0], seed=SEED) as multi:
+        bs = multi.bs_batch(spots, *G)["call"]
+        out, errors = [], []
+
+        def worker(k):
+            try:
+                for _ in range(5):
+                    r = multi.price_batch(spots, *G, 50.0, 40000.0) if k % 2 == 0 else multi.price_batch(spots[:5], *G, 50.0, 400000.0)
+                    out.append((len(r["call"]), r))
+            except Exception as e:      # pragma: no cover
+                errors.append(e)
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors and len(out) == 20
+        for n, r in out:
+            z = (r["call"] - bs[:n]) / np.maximum(r["call_se"], 1e-3)
+            assert np.all(np.isfinite(r["call"])) and np.abs(z).max() < 5.5
+        multi.set_seed(SEED)
+        a = multi.price_batch(spots, *G, 50.0, 40000.0)
+        multi.set_seed(SEED)
+        b = multi.price_batch(spots, *G, 50.0, 40000.0)
+        assert all(np.array_equal(a[k], b[k]) for k in a)
