@@ -274,6 +274,15 @@ __global__ void __launch_bounds__(kThreads, PayoffTraits<PAYOFF>::kCtasPerSm) si
     long long r = round_begin(w, R, W);
     const long long r_end = round_begin(w + 1, R, W);        // W <= R: never empty
     MCB_STAMP(0);
+#ifdef MCB_TRACE
+    if (a.trace && lane == 0) {                               // where this warp runs: SM, hardware warp slot, CTA, warp in CTA
+        unsigned smid_, warpid_;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid_));
+        a.trace[(size_t)w * 8 + 5] = ((unsigned long long)smid_ << 32) | warpid_;
+        a.trace[(size_t)w * 8 + 6] = ((unsigned long long)blockIdx.x << 32) | (unsigned)hw;
+    }
+#endif
 
     Xoshiro256 g;
     const size_t gtid = (size_t)w * 32 + lane;              // the generator stream belongs to the LOGICAL thread

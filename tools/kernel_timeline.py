@@ -146,7 +146,9 @@ def main():
         torch.cuda.synchronize()
         traced_us = 1e3 * a.elapsed_time(b)
         lib.mcb200_debug_set_trace(ctx._h, None)
-        t = trace.cpu().numpy().reshape(-1, 8)[:, :5].astype(np.float64)
+        raw = trace.cpu().numpy().reshape(-1, 8)
+        np.save(os.path.join(ROOT, "gpurun_out", "timeline_raw_%s.npy" % name), raw)
+        t = raw[:, :5].astype(np.float64)
         t0 = t[:, 0].min()
         rel = (t - t0) * 1e-3                                           # us
         pct = lambda x: [float(np.percentile(x, q)) for q in (0, 50, 90, 99, 100)]
