@@ -43,8 +43,8 @@ typedef enum {
 #define MCB200_ANTITHETIC 1u    /* call_price_av / put_price_av estimator (mc_simd.rs:82-149) */
 
 /* ------------------------------------------------------------------ context ------------------------------------ */
-/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per resident thread of
- * the price kernels: sm_count * ctas_per_sm * 256; the Greeks kernel uses the first grid_slots_greeks * 256 of them).
+/* One context = one device, one stream, one pool of per-thread xoshiro256++ substreams (one per LOGICAL thread of the
+ * largest launch plan: sm_count * ctas_per_sm * 256 resident threads x 6 waves; smaller plans use a prefix of it).
  * Thread slot i of the device uses substream jump^i(long_jump^substream_block(splitmix64(seed))): 2^128 draws per
  * thread, up to 2^40 thread slots per block, one block per GPU/rank, reached in O(log block) polynomial applications
  * (replaces per-chunk OS-entropy seeding, mc_simd.rs:52-54).  Launches continue their substreams.
@@ -77,20 +77,25 @@ typedef struct {
 } mcb200_info;
 int mcb200_ctx_info(mcb200_ctx *ctx, mcb200_info *out);
 
-/* Launch plan for one batch: how the work maps onto the resident warps.  Pure host logic.
+/* Launch plan for one batch: how the work maps onto the logical warps.  Pure host logic.
  * A "round" is 32 consecutive paths of one option (one per lane).  Round r belongs to option r / rounds_per_option;
  * logical warp w simulates rounds [w*R/W, (w+1)*R/W), R = total_rounds, W = warps, in order, and its lane l draws from
  * generator substream 32*w + l of the pool.  (Hardware warp h of CTA c is logical warp 8c + 2*(h%4) + h/4, so the two
- * warps of an SM sub-partition own neighbouring ranges.) */
+ * warps of an SM sub-partition own neighbouring ranges.)
+ * Small batches run as ONE wave: W = min(8 * grid_slots, R) resident warps.  Large batches are launched as up to 6 waves
+ * of CTAs (W = 8 * grid_slots * waves, every warp still owning >= 64 rounds): the SM's warp schedulers favour the CTA
+ * that became resident first, so a single wave tails off with one CTA per SM running alone; with several waves a fresh
+ * CTA takes every freed slot and only the last, short, wave tails off (1.5-2.7 % faster). */
 typedef struct {
     int n_paths;                 /* 8 * floor(num_trials / 8) */
     int half_steps;              /* floor(steps) / 2 */
     int rounds_per_option;       /* ceil(n_paths / 32) */
-    int warps;                   /* W = min(8 * grid_slots, total_rounds): every warp owns at least one round */
+    int warps;                   /* W = min(8 * grid_slots * waves, total_rounds): every warp owns at least one round */
     int grid;                    /* CTAs launched = ceil(W / 8) */
     int max_rounds_per_warp;     /* ceil(R / W): rounds differ by at most one between warps */
     int64_t total_rounds;        /* R = n_options * rounds_per_option */
     double path_steps;           /* n_options * n_paths * 2 * half_steps: the throughput numerator */
+    int waves;                   /* min(6, R / (8 * grid_slots * 64)), at least 1 */
 } mcb200_plan;
 int mcb200_plan_query(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan *out);
 int mcb200_plan_warp_range(const mcb200_plan *plan, int warp, int64_t *first_round, int64_t *end_round);

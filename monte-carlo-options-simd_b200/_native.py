@@ -35,7 +35,7 @@ class Info(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("n_paths", C.c_int), ("half_steps", C.c_int), ("rounds_per_option", C.c_int), ("warps", C.c_int),
                 ("grid", C.c_int), ("max_rounds_per_warp", C.c_int), ("total_rounds", C.c_int64),
-                ("path_steps", C.c_double)]
+                ("path_steps", C.c_double), ("waves", C.c_int)]
 
 
 class Shard(C.Structure):

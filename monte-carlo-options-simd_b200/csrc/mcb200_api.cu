@@ -124,7 +124,7 @@ struct mcb200_ctx {
     cudaStream_t stream = nullptr;
     uint64_t seed = 0;
     uint32_t block = 0;
-    uint64_t* pool = nullptr;     // grid_slots * kThreads states
+    uint64_t* pool = nullptr;     // grid_slots * kThreads * kPlanWaves states (one per logical thread of the largest plan)
     int64_t pool_threads = 0;
     uint64_t* d_jump = nullptr;   // jump polynomial table
     double* slots = nullptr; size_t slots_cap = 0;            // doubles: per (warp, option) partial moment sums
@@ -295,7 +295,8 @@ extern "C" int mcb200_ctx_create(mcb200_ctx** out, int device, uint64_t seed, ui
         c->ctas_per_sm = occ;
         c->grid_slots = c->sm_count * occ;
         c->grid_slots_greeks = c->sm_count * occ_greeks;
-        c->pool_threads = (int64_t)(c->grid_slots > c->grid_slots_greeks ? c->grid_slots : c->grid_slots_greeks) * kThreads;
+        c->pool_threads = (int64_t)(c->grid_slots > c->grid_slots_greeks ? c->grid_slots : c->grid_slots_greeks) * kThreads *
+                          kPlanWaves;                  // one substream per LOGICAL thread of a multi-wave launch
         if (dev_malloc((void**)&c->pool, (size_t)c->pool_threads * 32) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "pool alloc failed"); break; }
         if (cudaMalloc((void**)&c->d_jump, sizeof(XOSHIRO256_JUMP_POW2)) != cudaSuccess) { rc = fail(MCB200_ERR_NOMEM, "jump table alloc failed"); break; }
         if (cudaMemcpy(c->d_jump, XOSHIRO256_JUMP_POW2, sizeof(XOSHIRO256_JUMP_POW2), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(MCB200_ERR_CUDA, "jump table copy failed"); break; }

@@ -1,4 +1,4 @@
-// mcb200_plan.cpp -- launch planner: maps (options x trials) onto the resident warps.  Pure host logic, no CUDA.
+// mcb200_plan.cpp -- launch planner: maps (options x trials) onto the logical warps.  Pure host logic, no CUDA.
 //
 // The reference fans 8-path chunks of ONE option out over a thread pool (rayon, /root/reference/src/mc_simd.rs:49-51)
 // and prices options one call at a time (benches/benchmark.rs:40-42).  Here a whole batch is one launch.  The unit of
@@ -8,12 +8,26 @@
 // 1 option x 1e8 trials both fill all 148 SMs.  The kernel (mcb200_kernels.cuh) evaluates the same formulas.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include "../../include/mcb200.h"
 #include "mcb200_plan.h"
 
 namespace mcb200 {
 
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+// Waves of a launch: up to kPlanWaves, as many as leave every logical warp at least kWaveMinRounds rounds (small
+// batches: one wave, W = resident warps, as before).  MCB200_WAVES caps the count for tuning runs (tools/waves.sh).
+long long plan_waves(long long total_rounds, long long resident_warps) {
+    long long cap = kPlanWaves;
+    if (const char* env = std::getenv("MCB200_WAVES")) {
+        const long v = std::strtol(env, nullptr, 10);
+        if (v >= 1 && v <= kPlanWaves) cap = v;
+    }
+    long long waves = total_rounds / (resident_warps * kWaveMinRounds);
+    if (waves > cap) waves = cap;
+    return waves < 1 ? 1 : waves;
+}
 
 int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb200_plan* out) {
     if (!out || n_options < 0 || grid_slots <= 0) return MCB200_ERR_INVALID;
@@ -36,9 +50,16 @@ int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb2
     p.rounds_per_option = (int)ceil_div(n_paths, 32);
     p.total_rounds = (long long)n_options * p.rounds_per_option;
     // W <= R, so that every warp owns at least one round (the arrival counts of the kernel rely on it)
+    // Large batches are launched as several WAVES of CTAs (kPlanWaves times the resident count, each logical warp with
+    // its own generator substream): the SM's warp schedulers favour the CTA that became resident first, so with one
+    // wave the favoured CTAs finish at a third of the launch and the last one runs alone at the end; with several
+    // waves a fresh CTA takes every freed slot and only the last, short, wave tails off.
     const long long resident = (long long)grid_slots * kPlanWarps;
-    p.warps = (int)(p.total_rounds < resident ? p.total_rounds : resident);
+    const long long waves = plan_waves(p.total_rounds, resident);
+    const long long logical = resident * waves;
+    p.warps = (int)(p.total_rounds < logical ? p.total_rounds : logical);
     p.grid = (int)ceil_div(p.warps, kPlanWarps);
+    p.waves = (int)waves;
     p.max_rounds_per_warp = (int)ceil_div(p.total_rounds, p.warps);
     if (p.total_rounds > (1ll << 62) / p.warps) return MCB200_ERR_INVALID;   // (r+1)*W must fit in 64 bits
     *out = p;

@@ -72,7 +72,9 @@ def test_planner_reference_chunking(pkg):
             continue
         assert p["rounds_per_option"] == math.ceil(p["n_paths"] / 32)
         assert p["total_rounds"] == n * p["rounds_per_option"]
-        assert p["warps"] == min(8 * slots, p["total_rounds"]) and p["grid"] == math.ceil(p["warps"] / 8)
+        waves = max(1, min(6, p["total_rounds"] // (8 * slots * 64)))         # large batches: several waves of CTAs
+        assert p["waves"] == waves
+        assert p["warps"] == min(8 * slots * waves, p["total_rounds"]) and p["grid"] == math.ceil(p["warps"] / 8)
         assert p["max_rounds_per_warp"] == math.ceil(p["total_rounds"] / p["warps"])
         probe = range(p["warps"]) if p["warps"] <= 4096 else list(range(64)) + list(range(p["warps"] - 64, p["warps"]))
         prev_end, sizes = None, []
@@ -95,7 +97,7 @@ def test_planner_fills_the_machine(pkg):
     for n, steps, trials in [(1, 252.0, 1e6), (100000, 252.0, 1e4), (112, 100.0, 20000.0), (112, 1000.0, 2000.0),
                              (4096, 252.0, 1e5)]:
         p = pkg.plan_query(n, steps, trials, slots)
-        assert p["grid"] == slots
+        assert p["grid"] == slots * p["waves"] and (p["waves"] == 1 or p["total_rounds"] // p["warps"] >= 64)
         mean = p["total_rounds"] / p["warps"]
         assert p["max_rounds_per_warp"] < mean + 1
     c2 = pkg.plan_query(112, 100.0, 20000.0, slots)

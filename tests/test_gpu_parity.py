@@ -514,19 +514,28 @@ def test_gpu_agrees_with_scalar_mc_algorithm(ctx, oracle):
             assert abs(float(res[key][i]) - ref["mean"]) <= tol, (s, key, float(res[key][i]), ref)
 
 
-def test_long_segments_flush_in_fp64(ctx, oracle):
-    """One option, 7e8 one-pair paths: every warp walks > 4096 rounds of the same option, so its fp32 registers are
-    flushed to the fp64 slot several times (kMaxRoundsPerFlush) before the arrival.  The standard error is 5e-4, which
-    makes this the tightest check of the accumulation and of the fixed-order final sum over all 4736 segments."""
+def test_long_segments_flush_in_fp64(ctx, oracle, monkeypatch):
+    """One option, 7e8 one-pair paths as ONE wave of CTAs (MCB200_WAVES=1; the default plan would use six): every warp
+    walks > 4096 rounds of the same option, so its fp32 registers are flushed to the fp64 slot several times
+    (kMaxRoundsPerFlush) before the arrival.  The standard error is 5e-4, which makes this the tightest check of the
+    accumulation and of the fixed-order final sum over all 4736 segments."""
+    monkeypatch.setenv("MCB200_WAVES", "1")
     trials = 7.0e8
     plan = ctx.plan(1, 2.0, trials)
-    assert plan["max_rounds_per_warp"] > 4096 and plan["half_steps"] == 1
+    assert plan["max_rounds_per_warp"] > 4096 and plan["half_steps"] == 1 and plan["waves"] == 1
     res = ctx.price_batch([105.0], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 2.0, trials)
     for name, key in (("call_price", "call"), ("put_price", "put")):
         exact = oracle.bs64(name, 105.0, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
         n = plan["n_paths"]
         assert abs(res[key][0] * trials / n - exact) <= 3.5 * res[key + "_se"][0] + 2e-6 * exact, (key, res[key][0], exact)
         assert 2e-4 < res[key + "_se"][0] < 8e-4
+    # the same sample size through the default six-wave plan (28 416 segments): same law, other substreams
+    monkeypatch.delenv("MCB200_WAVES")
+    plan6 = ctx.plan(1, 2.0, trials)
+    assert plan6["waves"] == 6 and plan6["warps"] == 6 * plan["warps"]
+    res6 = ctx.price_batch([105.0], GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"], 2.0, trials)
+    exact = oracle.bs64("call_price", 105.0, GRID["strike"], GRID["vol"], GRID["r"], GRID["t"], GRID["q"])
+    assert abs(res6["call"][0] * trials / plan6["n_paths"] - exact) <= 3.5 * res6["call_se"][0] + 2e-6 * exact
 
 
 def test_plain_c_client_on_gpu(pkg, tmp_path):
