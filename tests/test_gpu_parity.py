@@ -184,23 +184,27 @@ def test_production_stream_per_path_parity(pkg, oracle):
             assert got["call"][o] == pytest.approx(want, rel=1e-5)
 
 
-def test_every_pool_substream_is_independent_on_the_device(pkg):
-    """One option spread over EVERY resident thread (4 rounds per warp), 6 steps = one triple per path, per-path sums
-    recovered from the dumped growth factors: unit variance per term, no correlation between consecutive paths of one
-    thread (serial), between neighbouring lanes, between neighbouring warps, between the first and the last warp of the
-    pool, nor in the squares -- over all 151 552 substreams of the pool, its last slots included."""
+@pytest.mark.parametrize("waves", [1, 6])
+def test_every_pool_substream_is_independent_on_the_device(pkg, waves):
+    """One option spread over EVERY logical thread of a plan, 6 steps = one triple per path, per-path sums recovered
+    from the dumped growth factors: unit variance per term, no correlation between consecutive paths of one thread
+    (serial), between neighbouring lanes, between neighbouring warps, between the first and the last warp, nor in the
+    squares.  waves = 1: the 151 552 resident threads, 4 rounds each; waves = 6: all 909 312 substreams of the pool
+    (its last slots included), 64 rounds each -- the plan of a large batch."""
     with pkg.Context(device=0, seed=99) as c:
         info = c.info()
-        warps = info["grid_slots"] * 8
-        n_paths = warps * 4 * 32
+        warps = info["grid_slots"] * 8 * waves
+        rounds = 4 if waves == 1 else 64
+        assert warps * 32 == info["pool_threads"] * waves // 6
+        n_paths = warps * rounds * 32
         plan = c.plan(1, 6.0, float(n_paths))
-        assert plan["warps"] == warps and plan["max_rounds_per_warp"] == 4 and plan["half_steps"] == 3
+        assert plan["warps"] == warps and plan["waves"] == waves and plan["max_rounds_per_warp"] == rounds and plan["half_steps"] == 3
         vol, t = 0.3, 1.0
         got = c.price_batch_dump([100.0], 100.0, vol, 0.0, t, 0.0, 6.0, float(n_paths))
     dt = t / 6.0
     drift = 6.0 * (-0.5 * vol * vol) * dt
     z = (np.log(got["growth"][0].astype(np.float64)) - drift) / (vol * math.sqrt(dt))      # sum of 6 unit normals
-    m = z.reshape(warps, 4, 32)                                                            # [warp][round][lane]
+    m = z.reshape(warps, rounds, 32)                                                       # [warp][round][lane]
     n = m.size
     assert abs(z.mean()) < 4.5 * math.sqrt(6.0 / n) and abs(z.var() / 6.0 - 1.0) < 4.5 * math.sqrt(2.0 / n)
     assert abs(((z / math.sqrt(6.0)) ** 4).mean() - 3.0) < 0.03                            # gaussian kurtosis
@@ -209,15 +213,15 @@ def test_every_pool_substream_is_independent_on_the_device(pkg):
         a, b = a.ravel() - a.mean(), b.ravel() - b.mean()
         return float((a * b).mean() / math.sqrt((a * a).mean() * (b * b).mean()))
     tol = lambda k: 4.5 / math.sqrt(k)
-    assert abs(corr(m[:, :-1, :], m[:, 1:, :])) < tol(n * 3 // 4)                         # serial, same thread
+    assert abs(corr(m[:, :-1, :], m[:, 1:, :])) < tol(n * (rounds - 1) // rounds)         # serial, same thread
     assert abs(corr(m[:, :, :-1], m[:, :, 1:])) < tol(n * 31 // 32)                       # neighbouring lanes
     assert abs(corr(m[:-1], m[1:])) < tol(n)                                               # neighbouring warps
-    assert abs(corr(m[:64], m[-64:])) < tol(64 * 128)                                      # both ends of the pool
-    assert abs(corr(m[:, :-1, :] ** 2, m[:, 1:, :] ** 2)) < tol(n * 3 // 4)
+    assert abs(corr(m[:64], m[-64:])) < tol(64 * rounds * 32)                              # both ends of the plan's substreams
+    assert abs(corr(m[:, :-1, :] ** 2, m[:, 1:, :] ** 2)) < tol(n * (rounds - 1) // rounds)
     assert abs(corr(m[:, :, :-1] ** 2, m[:, :, 1:] ** 2)) < tol(n * 31 // 32)
-    # per-thread means over the 4 paths of each thread: no thread is an outlier beyond what 151 552 normals allow
-    per_thread = m.mean(axis=1).ravel() / math.sqrt(6.0 / 4.0)
-    assert np.abs(per_thread).max() < 5.6
+    # per-thread means over the paths of each thread: no thread is an outlier beyond what ~1e6 normals allow
+    per_thread = m.mean(axis=1).ravel() / math.sqrt(6.0 / rounds)
+    assert np.abs(per_thread).max() < 6.0
 
 
 # ---------------------------------------------------------------------------------------------- reference tests replayed
