@@ -85,7 +85,8 @@ int mcb200_ctx_info(mcb200_ctx *ctx, mcb200_info *out);
  * Small batches run as ONE wave: W = min(8 * grid_slots, R) resident warps.  Large batches are launched as up to 6 waves
  * of CTAs (W = 8 * grid_slots * waves, every warp still owning >= 64 rounds): the SM's warp schedulers favour the CTA
  * that became resident first, so a single wave tails off with one CTA per SM running alone; with several waves a fresh
- * CTA takes every freed slot and only the last, short, wave tails off (1.5-2.7 % faster). */
+ * CTA takes every freed slot and only the last, short, wave tails off (1.5-2.7 % faster).  The environment variable
+ * MCB200_WAVES=1..6 caps the wave count (tuning and tests; it changes the plan, hence which substream draws which path). */
 typedef struct {
     int n_paths;                 /* 8 * floor(num_trials / 8) */
     int half_steps;              /* floor(steps) / 2 */

@@ -3,7 +3,7 @@
 // The reference fans 8-path chunks of ONE option out over a thread pool (rayon, /root/reference/src/mc_simd.rs:49-51)
 // and prices options one call at a time (benches/benchmark.rs:40-42).  Here a whole batch is one launch.  The unit of
 // work is a "round": 32 consecutive paths of one option (one per lane of a warp).  The n_options * ceil(n_paths/32)
-// rounds are dealt to the W resident warps in contiguous ranges  [w*R/W, (w+1)*R/W)  -- equal to within one round --
+// rounds are dealt to the W logical warps in contiguous ranges  [w*R/W, (w+1)*R/W)  -- equal to within one round --
 // so the load of every SM sub-partition is the same whatever the shape of the batch: 1e5 options x 1e4 trials and
 // 1 option x 1e8 trials both fill all 148 SMs.  The kernel (mcb200_kernels.cuh) evaluates the same formulas.
 #include <cmath>
@@ -49,7 +49,7 @@ int make_plan(int n_options, float steps, float num_trials, int grid_slots, mcb2
     }
     p.rounds_per_option = (int)ceil_div(n_paths, 32);
     p.total_rounds = (long long)n_options * p.rounds_per_option;
-    // W <= R, so that every warp owns at least one round (the arrival counts of the kernel rely on it)
+    // W <= R, so that every warp owns at least one round (the arrival counts of the kernel rely on it).
     // Large batches are launched as several WAVES of CTAs (kPlanWaves times the resident count, each logical warp with
     // its own generator substream): the SM's warp schedulers favour the CTA that became resident first, so with one
     // wave the favoured CTAs finish at a third of the launch and the last one runs alone at the end; with several
