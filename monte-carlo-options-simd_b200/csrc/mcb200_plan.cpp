@@ -24,7 +24,12 @@ long long plan_waves(long long total_rounds, long long resident_warps) {
         const long v = std::strtol(env, nullptr, 10);
         if (v >= 1 && v <= kPlanWaves) cap = v;
     }
-    long long waves = total_rounds / (resident_warps * kWaveMinRounds);
+    long long min_rounds = kWaveMinRounds;
+    if (const char* env = std::getenv("MCB200_WAVE_MIN_ROUNDS")) {
+        const long v = std::strtol(env, nullptr, 10);
+        if (v >= 1) min_rounds = v;
+    }
+    long long waves = total_rounds / (resident_warps * min_rounds);
     if (waves > cap) waves = cap;
     return waves < 1 ? 1 : waves;
 }
